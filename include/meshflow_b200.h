@@ -1,0 +1,139 @@
+/*
+ * meshflow_b200 -- C ABI of the B200-native MeshFlow stabilization core.
+ *
+ * The reference (how4rd/meshflow, meshflowstabilizer.py, cited below as mfs.py:N) has no FFI of its
+ * own: its boundary is the Python class MeshFlowStabilizer.  Each entry point below replaces the body
+ * of one of the private stage methods that stabilize() (mfs.py:102-169) calls; the Python host side
+ * (meshflow_b200/stabilizer.py) keeps the reference's method names and signatures and binds these
+ * symbols with ctypes (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a contiguous array owned by the caller;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing and
+ *     never synchronises; scratch memory is passed in as `workspace` (size from the *_workspace_bytes
+ *     query of the same stage);
+ *   - return value: 0 on success, a negative MF_E_* code otherwise; mf_last_error() then returns a
+ *     thread-local, human-readable message;
+ *   - V = (R+1)*(C+1) mesh vertices in row-major order (row outer, column inner), exactly the order
+ *     of _get_vertex_x_y (mfs.py:881-906);
+ *   - "definition" is the reference's ADAPTIVE_WEIGHTS_DEFINITION_* value 0..3 (mfs.py:32-35).
+ */
+#ifndef MESHFLOW_B200_H
+#define MESHFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_OK 0
+#define MF_E_INVALID (-1)   /* bad argument (null pointer, non-positive size, unknown definition) */
+#define MF_E_WORKSPACE (-2) /* workspace too small */
+#define MF_E_LAUNCH (-3)    /* CUDA launch / runtime error (message holds cudaGetErrorString) */
+#define MF_E_UNSUPPORTED (-4) /* size outside what the kernels are built for */
+
+/* Library / build identification.  mf_version() = 10000*major + 100*minor + patch. */
+int mf_version(void);
+/* Compute capability the embedded cubin was built for (100 for sm_100a). */
+int mf_built_for_sm(void);
+const char* mf_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Vertex-motion estimation -- replaces _get_unstabilized_vertex_velocities (mfs.py:287-362) minus
+ *     the host OpenCV matching, _get_vertex_nearby_feature_residual_velocities (mfs.py:365-452) and
+ *     the prefix sum of _get_unstabilized_vertex_displacements_and_homographies (mfs.py:268-284),
+ *     batched over P frame pairs.
+ *
+ * Features arrive UN-compacted, as the host tracker produced them; `keep` applies the LK status mask
+ * (mfs.py:622-624) and the per-subframe RANSAC inlier mask (mfs.py:569-574) on the device.
+ *   early_xy, late_xy : [N,2] float32, subframe-relative coordinates of all tracked candidates
+ *   offset_xy         : [N,2] int32, top-left corner of the feature's subframe (mfs.py:509, 578)
+ *   keep              : [N] uint8, 1 = survives both masks
+ *   pair_start        : [P+1] int32, features of pair p are [pair_start[p], pair_start[p+1])
+ *   max_pair_features : upper bound of pair_start[p+1]-pair_start[p]; only sizes the shared-memory
+ *                       candidate lists (a too-small value costs speed, never correctness)
+ *   homographies      : [P,9] float64, global early->late homography of each pair (mfs.py:524)
+ *   vertex_xy         : [V,2] float32 rest positions (mfs.py:881-906)
+ *   vel_out           : [P,V,2] float32 vertex velocities after both median filters
+ *   assign_count_out  : optional [P,V] int32, number of features assigned to each vertex (parity of
+ *                       the feature->vertex assignment); may be NULL
+ * ---------------------------------------------------------------------------------------------- */
+size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int C);
+int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t* offset_xy,
+                     const uint8_t* keep, const int32_t* pair_start, int64_t N, int P,
+                     int max_pair_features,
+                     const double* homographies, const float* vertex_xy,
+                     int W, int H, int R, int C, int ellipse_rows, int ellipse_cols,
+                     float* vel_out, int32_t* assign_count_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* disp[0] = 0, disp[t+1] = disp[t] + (double)vel[t]  -- sequential float64 scan (mfs.py:271, 281).
+ *   vel: [P, n] float32, disp: [P+1, n] float64, n = 2V.  An optional `disp0` [n] float64 seeds
+ *   disp[0] (frame-sharded callers chain shards with it); NULL means zeros. */
+int mf_prefix_displacements(const float* vel, const double* disp0, double* disp, int P, int64_t n,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Jacobi path optimisation -- replaces _get_stabilized_vertex_displacements (mfs.py:632-710),
+ *     _get_jacobi_method_input (713-783), _get_adaptive_weights (786-841) and
+ *     _get_jacobi_method_output (844-878).  Band-limited restatement of the dense system; the
+ *     adaptive weight lambda_t is computed on the device from `homographies`.
+ *   u, s          : [F, n_sys] float64, n_sys = 2V systems (vertex-major, x/y interleaved); systems
+ *                   [sys_begin, sys_end) are solved (vertex sharding), the rest of `s` is untouched
+ *   homographies  : [F,9] float64 (last one identity, mfs.py:273-274)
+ *   lambda_out    : optional [F] float64 copy of the adaptive weights; may be NULL
+ * ---------------------------------------------------------------------------------------------- */
+size_t mf_jacobi_workspace_bytes(int F, int64_t n_sys);
+int mf_jacobi_solve(const double* u, const double* homographies, double* s, int F, int64_t n_sys,
+                    int64_t sys_begin, int64_t sys_end, int W, int H, int radius, int iterations,
+                    int definition, double* lambda_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Mesh warp + crop -- replaces _get_stabilized_frames_and_crop_boundaries (mfs.py:909-1108).
+ *   frames_in   : [nf, H, W, 3] uint8 BGR
+ *   u, s        : [nf, V, 2] float64 displacements OF THESE nf FRAMES (caller passes its shard)
+ *   vertex_xy   : [V,2] float32
+ *   frames_out  : [nf, H, W, 3] uint8 stabilized frames (cv2.remap fixed-point bilinear, constant
+ *                 border b,g,r)
+ *   crop_out    : [nf,4] int32 per-frame (left, top, right, bottom) (mfs.py:1075-1098); the caller
+ *                 combines them with max/max/min/min (mfs.py:1103-1106; an all-reduce when sharded)
+ *   map_out     : optional [nf, H, W, 2] float32 (map_x, map_y) for parity checks; may be NULL
+ * ---------------------------------------------------------------------------------------------- */
+size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C);
+int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s, const float* vertex_xy,
+                   int nf, int W, int H, int R, int C, int border_b, int border_g, int border_r,
+                   uint8_t* frames_out, int32_t* crop_out, float* map_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Crop rectangle (inclusive) stretched back to W x H -- replaces _crop_frames (mfs.py:1111-1157);
+ * cv2.resize INTER_LINEAR 11-bit fixed point. */
+size_t mf_crop_resize_workspace_bytes(int W, int H);
+int mf_crop_resize(const uint8_t* frames_in, int nf, int W, int H, int left, int top, int right,
+                   int bottom, uint8_t* frames_out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Device-side crop plumbing, so that a step never waits for the host (and so that the multi-GPU
+ * combine is one ncclMax all-reduce on the same 4 ints):
+ *   mf_crop_combine       : per-frame edges [nf,4] -> crop_enc_out[4] = [max left, max top, -min right,
+ *                           -min bottom]  (mfs.py:1103-1106 as a single max-reduction)
+ *   mf_crop_resize_device : mf_crop_resize with the rectangle read from device memory in that
+ *                           encoding; an empty / out-of-frame rectangle leaves frames_out untouched
+ *                           (the host raises when it reads the rectangle back). */
+int mf_crop_combine(const int32_t* per_frame_crop, int nf, int32_t* crop_enc_out, void* stream);
+int mf_crop_resize_device(const uint8_t* frames_in, int nf, int W, int H, const int32_t* crop_enc,
+                          uint8_t* frames_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stability score -- replaces _compute_stability_score (mfs.py:1216-1259): per system the energy of
+ * DFT bins 1..5 of the frame-to-frame differences over the total energy (Parseval).
+ *   s : [F, n_sys] float64;  ratio_out : [n_sys] float64 (caller averages x and y systems).
+ * ---------------------------------------------------------------------------------------------- */
+int mf_stability_ratios(const double* s, int F, int64_t n_sys, double* ratio_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHFLOW_B200_H */

@@ -1,0 +1,268 @@
+// Jacobi path optimisation on the device (hot-path subsystem 2).
+//
+// The reference builds two dense F x F matrices and runs K sweeps of two dense mat-muls per vertex
+// (mfs.py:713-783, 844-878).  The system is banded: element form
+//     x'[t] = (1/diag[t]) * ( b[t] + 2*lambda[t] * sum_{|k| <= radius, 0 <= t+k < F} w[k] * x[t+k] )
+// with w[k] = exp(-((3/radius) k)^2) INCLUDING k = 0, diag[t] = 1 + 2 lambda[t] sum_{r=0}^{F-1} w[t-r]
+// over ALL frames (both quirks of the reference are kept).
+//
+//   jacobi_coeff_kernel : lambda[t] from the global homography (mfs.py:786-841), 1/diag[t].
+//   jacobi_solve_kernel : persistent -- one CTA owns the x and y trajectories of one vertex
+//                         (double2 per frame), keeps them in shared memory with `radius` zero cells
+//                         of padding on either side (so the boundary needs no branches), and runs
+//                         every sweep without leaving the SM: HBM is touched twice (load b, store x).
+#include "mf_common.cuh"
+#include "mf_math.cuh"
+
+namespace mf {
+
+__global__ void __launch_bounds__(128) jacobi_coeff_kernel(const double* __restrict__ homographies, int F,
+                                                           int W, int H, int radius, int definition,
+                                                           double* __restrict__ inv_diag,
+                                                           double* __restrict__ two_lambda,
+                                                           double* __restrict__ lambda_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= F) return;
+  const double lam = adaptive_lambda(homographies + (size_t)t * 9, W, H, definition);
+  // exp(-(3k/radius)^2) underflows to exactly 0 beyond |k| ~ 9.1 radius: summing 10 radius either
+  // side equals the reference's sum over all frames.
+  const double c = 3.0 / (double)radius;
+  const int reach = 10 * radius + 1;
+  const int lo = max(0, t - reach), hi = min(F - 1, t + reach);
+  double sum = 0.0;
+  for (int r = lo; r <= hi; ++r) {
+    const double a = c * (double)(t - r);
+    sum += exp(-(a * a));
+  }
+  const double diag = 1.0 + 2.0 * (lam * sum);
+  inv_diag[t] = 1.0 / diag;
+  two_lambda[t] = 2.0 * lam;
+  if (lambda_out) lambda_out[t] = lam;
+}
+
+// One CTA per vertex.  PT = frames per thread (strided by blockDim so that shared-memory reads of
+// neighbouring threads are neighbouring double2 cells).  RADIUS > 0: compile-time radius, weights in
+// registers; RADIUS == 0: run-time radius, weights in shared memory.
+template <int RADIUS, int PT>
+__global__ void __launch_bounds__(512) jacobi_solve_kernel(
+    const double* __restrict__ u, double* __restrict__ s, int F, int64_t n_sys, int64_t sys_begin,
+    int radius_rt, int iterations, const double* __restrict__ inv_diag,
+    const double* __restrict__ two_lambda) {
+  extern __shared__ double2 xs_raw[];  // [F + 2 radius] trajectory, then (generic) [2 radius + 1] weights
+  const int radius = RADIUS > 0 ? RADIUS : radius_rt;
+  double2* xs = xs_raw + radius;  // xs[t], t in [-radius, F + radius)
+  double* wsm = reinterpret_cast<double*>(xs_raw + F + 2 * radius);
+  const int64_t q = sys_begin + 2 * (int64_t)blockIdx.x;  // first of the two systems (x, y)
+  const int nt = blockDim.x, tid = threadIdx.x;
+
+  double wreg[RADIUS > 0 ? 2 * RADIUS + 1 : 1];
+  const double c = 3.0 / (double)radius;
+  if (RADIUS > 0) {
+#pragma unroll
+    for (int k = 0; k < 2 * RADIUS + 1; ++k) {
+      const double a = c * (double)(k - RADIUS);
+      wreg[k] = exp(-(a * a));
+    }
+  } else {
+    for (int k = tid; k < 2 * radius + 1; k += nt) {
+      const double a = c * (double)(k - radius);
+      wsm[k] = exp(-(a * a));
+    }
+  }
+  for (int k = tid; k < radius; k += nt) {
+    xs[-1 - k] = make_double2(0.0, 0.0);
+    xs[F + k] = make_double2(0.0, 0.0);
+  }
+  double2 b[PT];
+  double invd[PT], twol[PT];
+#pragma unroll
+  for (int j = 0; j < PT; ++j) {
+    const int t = tid + j * nt;
+    if (t < F) {
+      b[j] = *reinterpret_cast<const double2*>(u + (size_t)t * n_sys + q);
+      invd[j] = inv_diag[t];
+      twol[j] = two_lambda[t];
+      xs[t] = b[j];
+    } else {
+      b[j] = make_double2(0.0, 0.0); invd[j] = 0.0; twol[j] = 0.0;
+    }
+  }
+  __syncthreads();
+  for (int it = 0; it < iterations; ++it) {
+    double2 nv[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const int t = tid + j * nt;
+      double ax = 0.0, ay = 0.0;
+      if (t < F) {
+        const double2* win = xs + t - radius;
+        if (RADIUS > 0) {
+#pragma unroll
+          for (int k = 0; k < 2 * RADIUS + 1; ++k) {
+            const double2 v = win[k];
+            ax = fma(wreg[k], v.x, ax);
+            ay = fma(wreg[k], v.y, ay);
+          }
+        } else {
+          for (int k = 0; k < 2 * radius + 1; ++k) {
+            const double2 v = win[k];
+            const double w = wsm[k];
+            ax = fma(w, v.x, ax);
+            ay = fma(w, v.y, ay);
+          }
+        }
+      }
+      nv[j].x = invd[j] * fma(twol[j], ax, b[j].x);
+      nv[j].y = invd[j] * fma(twol[j], ay, b[j].y);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const int t = tid + j * nt;
+      if (t < F) xs[t] = nv[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < PT; ++j) {
+    const int t = tid + j * nt;
+    if (t < F) *reinterpret_cast<double2*>(s + (size_t)t * n_sys + q) = xs[t];
+  }
+}
+
+// Large-F variant: the per-frame constants do not fit in registers next to the staged sweep, so
+// b / inv_diag / two_lambda are re-read (L1/L2 resident) every sweep.
+template <int RADIUS>
+__global__ void __launch_bounds__(512) jacobi_solve_long_kernel(
+    const double* __restrict__ u, double* __restrict__ s, int F, int64_t n_sys, int64_t sys_begin,
+    int radius_rt, int iterations, const double* __restrict__ inv_diag,
+    const double* __restrict__ two_lambda) {
+  constexpr int PT = 20;  // 512 threads x 20 frames = 10240 frames
+  extern __shared__ double2 xs_raw[];
+  const int radius = RADIUS > 0 ? RADIUS : radius_rt;
+  double2* xs = xs_raw + radius;
+  double* wsm = reinterpret_cast<double*>(xs_raw + F + 2 * radius);
+  const int64_t q = sys_begin + 2 * (int64_t)blockIdx.x;
+  const int nt = blockDim.x, tid = threadIdx.x;
+  const double c = 3.0 / (double)radius;
+  for (int k = tid; k < 2 * radius + 1; k += nt) {
+    const double a = c * (double)(k - radius);
+    wsm[k] = exp(-(a * a));
+  }
+  for (int k = tid; k < radius; k += nt) {
+    xs[-1 - k] = make_double2(0.0, 0.0);
+    xs[F + k] = make_double2(0.0, 0.0);
+  }
+  for (int t = tid; t < F; t += nt) xs[t] = *reinterpret_cast<const double2*>(u + (size_t)t * n_sys + q);
+  __syncthreads();
+  for (int it = 0; it < iterations; ++it) {
+    double2 nv[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const int t = tid + j * nt;
+      if (t < F) {
+        const double2* win = xs + t - radius;
+        double ax = 0.0, ay = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < 2 * radius + 1; ++k) {
+          const double2 v = win[k];
+          const double w = wsm[k];
+          ax = fma(w, v.x, ax);
+          ay = fma(w, v.y, ay);
+        }
+        const double2 bb = __ldg(reinterpret_cast<const double2*>(u + (size_t)t * n_sys + q));
+        const double id = __ldg(inv_diag + t), tl = __ldg(two_lambda + t);
+        nv[j].x = id * fma(tl, ax, bb.x);
+        nv[j].y = id * fma(tl, ay, bb.y);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const int t = tid + j * nt;
+      if (t < F) xs[t] = nv[j];
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < F; t += nt) *reinterpret_cast<double2*>(s + (size_t)t * n_sys + q) = xs[t];
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(MF_E_LAUNCH, "jacobi: shared memory opt-in (%zu B): %s", bytes,
+                                      cudaGetErrorString(e));
+  }
+  return MF_OK;
+}
+
+template <int RADIUS>
+static int launch_solve(const double* u, double* s, int F, int64_t n_sys, int64_t sys_begin, int64_t n_vert,
+                        int radius, int iterations, const double* inv_diag, const double* two_lambda,
+                        cudaStream_t st) {
+  const size_t smem = (size_t)(F + 2 * radius) * sizeof(double2) + (size_t)(2 * radius + 1) * sizeof(double);
+  if (smem > 227 * 1024)
+    return fail(MF_E_UNSUPPORTED, "jacobi: F=%d radius=%d needs %zu B of shared memory per vertex (max 232448)",
+                F, radius, smem);
+  const dim3 grid((unsigned)n_vert);
+  if (F <= 512) {
+    const int nt = (F + 31) / 32 * 32;
+    auto k = jacobi_solve_kernel<RADIUS, 1>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<grid, nt, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
+  } else if (F <= 1024) {
+    const int nt = ((F + 1) / 2 + 31) / 32 * 32;
+    auto k = jacobi_solve_kernel<RADIUS, 2>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<grid, nt, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
+  } else if (F <= 2048) {
+    const int nt = ((F + 3) / 4 + 31) / 32 * 32;
+    auto k = jacobi_solve_kernel<RADIUS, 4>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<grid, nt, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
+  } else {
+    if (F > 20 * 512) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds 10240 frames per solve", F);
+    auto k = jacobi_solve_long_kernel<0>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<grid, 512, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
+  }
+  return check_launch("jacobi_solve");
+}
+
+}  // namespace mf
+
+extern "C" size_t mf_jacobi_workspace_bytes(int F, int64_t n_sys) {
+  (void)n_sys;
+  if (F <= 0) return 0;
+  return 2 * mf::align_up((size_t)F * sizeof(double), 256);
+}
+
+extern "C" int mf_jacobi_solve(const double* u, const double* homographies, double* s, int F, int64_t n_sys,
+                               int64_t sys_begin, int64_t sys_end, int W, int H, int radius, int iterations,
+                               int definition, double* lambda_out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  MF_REQUIRE(u && homographies && s && workspace, "mf_jacobi_solve: null pointer");
+  MF_REQUIRE(F > 0 && n_sys > 0 && W > 0 && H > 0, "mf_jacobi_solve: bad sizes");
+  MF_REQUIRE(radius > 0 && iterations >= 0, "mf_jacobi_solve: radius must be positive, iterations >= 0");
+  MF_REQUIRE(definition >= 0 && definition <= 3,
+             "mf_jacobi_solve: invalid adaptive_weights_definition %d (expected 0..3)", definition);
+  MF_REQUIRE((n_sys % 2) == 0 && (sys_begin % 2) == 0 && (sys_end % 2) == 0,
+             "mf_jacobi_solve: systems come in (x, y) pairs; n_sys, sys_begin, sys_end must be even");
+  MF_REQUIRE(0 <= sys_begin && sys_begin <= sys_end && sys_end <= n_sys, "mf_jacobi_solve: bad system range");
+  if (workspace_bytes < mf_jacobi_workspace_bytes(F, n_sys))
+    return mf::fail(MF_E_WORKSPACE, "mf_jacobi_solve: workspace %zu < %zu bytes", workspace_bytes,
+                    mf_jacobi_workspace_bytes(F, n_sys));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* inv_diag = (double*)workspace;
+  double* two_lambda = (double*)((char*)workspace + mf::align_up((size_t)F * sizeof(double), 256));
+  mf::jacobi_coeff_kernel<<<(F + 127) / 128, 128, 0, st>>>(homographies, F, W, H, radius, definition,
+                                                          inv_diag, two_lambda, lambda_out);
+  if (int e = mf::check_launch("jacobi_coeff")) return e;
+  const int64_t n_vert = (sys_end - sys_begin) / 2;
+  if (n_vert == 0) return MF_OK;
+  if (n_vert > 2147483647LL) return mf::fail(MF_E_UNSUPPORTED, "mf_jacobi_solve: too many vertices");
+  if (radius == 10)
+    return mf::launch_solve<10>(u, s, F, n_sys, sys_begin, n_vert, radius, iterations, inv_diag, two_lambda, st);
+  return mf::launch_solve<0>(u, s, F, n_sys, sys_begin, n_vert, radius, iterations, inv_diag, two_lambda, st);
+}

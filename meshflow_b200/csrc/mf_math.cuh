@@ -1,0 +1,377 @@
+// Per-element arithmetic of the MeshFlow hot path, shared by every kernel.
+//
+// Everything that DECIDES an integer (feature->vertex membership, cell membership, 1/32-px source
+// coordinates, crop edges, fixed-point blends) is written with explicit round-to-nearest
+// multiply/add/divide so that nvcc can never contract it into an FMA: the reference computes these in
+// plain IEEE double (NumPy / OpenCV scalar paths), and an FMA changes the last bit.  The functions are
+// __host__ __device__ so that the CPU-only test-suite can drive the very same code through
+// tests/hostemu (g++ -ffp-contract=off); the shipped library only ever runs them on the GPU.
+//
+// Reference line numbers are for how4rd/meshflow's meshflowstabilizer.py ("mfs.py").
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MF_HD __host__ __device__ __forceinline__
+#else
+#define MF_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define MF_MUL(a, b) __dmul_rn((a), (b))
+#define MF_ADD(a, b) __dadd_rn((a), (b))
+#define MF_SUB(a, b) __dsub_rn((a), (b))
+#define MF_DIV(a, b) __ddiv_rn((a), (b))
+#define MF_SQRT(a) __dsqrt_rn((a))
+#define MF_FMUL(a, b) __fmul_rn((a), (b))
+#define MF_FADD(a, b) __fadd_rn((a), (b))
+#define MF_FSUB(a, b) __fsub_rn((a), (b))
+#else
+#define MF_MUL(a, b) ((a) * (b))
+#define MF_ADD(a, b) ((a) + (b))
+#define MF_SUB(a, b) ((a) - (b))
+#define MF_DIV(a, b) ((a) / (b))
+#define MF_SQRT(a) sqrt((a))
+#define MF_FMUL(a, b) ((a) * (b))
+#define MF_FADD(a, b) ((a) + (b))
+#define MF_FSUB(a, b) ((a) - (b))
+#endif
+
+#define MF_INT_MIN (-2147483647 - 1)
+#define MF_INT_MAX 2147483647
+
+namespace mf {
+
+// ---------------------------------------------------------------------------------------------
+// rounding helpers
+// ---------------------------------------------------------------------------------------------
+// cvRound / saturate_cast<int>(double): round half to even, clamp, NaN -> INT_MIN.
+MF_HD int round_sat(double v) {
+  if (!(v == v)) return MF_INT_MIN;
+  if (v <= -2147483648.0) return MF_INT_MIN;
+  if (v >= 2147483647.0) return MF_INT_MAX;
+#if defined(__CUDA_ARCH__)
+  return __double2int_rn(v);
+#else
+  return (int)nearbyint(v);
+#endif
+}
+
+MF_HD int round_sat_f(float v) {
+  if (!(v == v)) return MF_INT_MIN;
+  if (v <= -2147483648.0f) return MF_INT_MIN;
+  if (v >= 2147483520.0f) return MF_INT_MAX;
+#if defined(__CUDA_ARCH__)
+  return __float2int_rn(v);
+#else
+  return (int)nearbyintf(v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv2.perspectiveTransform, float64 arithmetic:  w = 1/w (0 when |w| <= DBL_EPSILON), then multiply.
+// (mfs.py:325, 420, 1054)
+// ---------------------------------------------------------------------------------------------
+MF_HD void persp(const double* M, double x, double y, double& ox, double& oy) {
+  double w = MF_ADD(MF_ADD(MF_MUL(x, M[6]), MF_MUL(y, M[7])), M[8]);
+  w = (fabs(w) > 2.220446049250313e-16) ? MF_DIV(1.0, w) : 0.0;
+  ox = MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, M[0]), MF_MUL(y, M[1])), M[2]), w);
+  oy = MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, M[3]), MF_MUL(y, M[4])), M[5]), w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Feature -> vertex membership (mfs.py:426-446).  For a feature at (fx, fy) returns the inclusive
+// row window [top, bot]; col_range() gives the inclusive column range of one row in that window.
+// ---------------------------------------------------------------------------------------------
+struct FeatureCell {
+  double frow, fcol;
+  int top, bot;
+};
+
+MF_HD FeatureCell feature_cell(double fx, double fy, int W, int H, int R, int C, int er) {
+  FeatureCell f;
+  f.frow = MF_MUL(MF_DIV(fy, (double)H), (double)R);
+  f.fcol = MF_MUL(MF_DIV(fx, (double)W), (double)C);
+  const double half_rows = MF_DIV((double)er, 2.0);
+  double t = ceil(MF_SUB(f.frow, half_rows));
+  double b = floor(MF_ADD(f.frow, half_rows));
+  // clamp in double first so that wild coordinates cannot overflow the int conversion
+  t = t < 0.0 ? 0.0 : (t > (double)(R + 1) ? (double)(R + 1) : t);
+  b = b > (double)R ? (double)R : (b < -1.0 ? -1.0 : b);
+  f.top = (int)t;
+  f.bot = (int)b;
+  return f;
+}
+
+MF_HD void col_range(const FeatureCell& f, int vr, int C, int er, int ec, int& left, int& right) {
+  const double q = MF_DIV(MF_SUB((double)vr, f.frow), (double)er);
+  double arg = MF_SUB(0.25, MF_MUL(q, q));
+  if (arg < 0.0) arg = 0.0;  // the reference would raise; cannot happen inside [top, bot]
+  const double half = MF_MUL((double)ec, MF_SQRT(arg));
+  double l = ceil(MF_SUB(f.fcol, half));
+  double r = floor(MF_ADD(f.fcol, half));
+  l = l < 0.0 ? 0.0 : (l > (double)(C + 1) ? (double)(C + 1) : l);
+  r = r > (double)C ? (double)C : (r < -1.0 ? -1.0 : r);
+  left = (int)l;
+  right = (int)r;
+}
+
+// Order-preserving map double -> uint64 (radix select of the per-vertex medians).
+MF_HD uint64_t key_of(double v) {
+  uint64_t b;
+#if defined(__CUDA_ARCH__)
+  b = (uint64_t)__double_as_longlong(v);
+#else
+  union { double d; uint64_t u; } cv; cv.d = v; b = cv.u;
+#endif
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+MF_HD double value_of(uint64_t k) {
+  uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  union { double d; uint64_t u; } cv; cv.u = b; return cv.d;
+#endif
+}
+
+// median of 9 floats (cv2.medianBlur ksize 3, mfs.py:359-360)
+MF_HD void sort2f(float& a, float& b) { float lo = a < b ? a : b; float hi = a < b ? b : a; a = lo; b = hi; }
+MF_HD float median9(float* v) {
+  sort2f(v[1], v[2]); sort2f(v[4], v[5]); sort2f(v[7], v[8]);
+  sort2f(v[0], v[1]); sort2f(v[3], v[4]); sort2f(v[6], v[7]);
+  sort2f(v[1], v[2]); sort2f(v[4], v[5]); sort2f(v[7], v[8]);
+  sort2f(v[0], v[3]); sort2f(v[5], v[8]); sort2f(v[4], v[7]);
+  sort2f(v[3], v[6]); sort2f(v[1], v[4]); sort2f(v[2], v[5]);
+  sort2f(v[4], v[7]); sort2f(v[4], v[2]); sort2f(v[6], v[4]);
+  sort2f(v[4], v[2]);
+  return v[4];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adaptive weight lambda_t (mfs.py:786-841): eigenvalue magnitudes of [[a,b,tx],[c,d,ty],[0,0,1]]
+// are 1 and those of the 2x2 block.
+// ---------------------------------------------------------------------------------------------
+MF_HD double adaptive_lambda(const double* Hm, int W, int H, int definition) {
+  if (definition == 2) return 100.0;
+  if (definition == 3) return 1.0;
+  const double a = Hm[0], b = Hm[1], tx = Hm[2], c = Hm[3], d = Hm[4], ty = Hm[5];
+  const double tr = a + d;
+  const double det = a * d - b * c;
+  const double disc = tr * tr - 4.0 * det;
+  double m1, m2;
+  if (disc >= 0.0) {
+    const double sq = sqrt(disc);
+    m1 = fabs((tr + sq) / 2.0);
+    m2 = fabs((tr - sq) / 2.0);
+  } else {
+    m1 = m2 = sqrt(fabs(det));
+  }
+  // sort {1, m1, m2} ascending -> ratio = middle / largest
+  double lo = 1.0, mid = m1, hi = m2, t;
+  if (lo > mid) { t = lo; lo = mid; mid = t; }
+  if (mid > hi) { t = mid; mid = hi; hi = t; }
+  if (lo > mid) { t = lo; lo = mid; mid = t; }
+  const double ratio = mid / hi;
+  const double qx = tx / (double)W, qy = ty / (double)H;
+  const double trans = sqrt(qx * qx + qy * qy);
+  const double c1 = -1.93 * trans + 0.95;
+  const double c2 = (definition == 0) ? 5.83 * ratio + 4.88 : 5.83 * ratio - 4.88;
+  const double m = c1 < c2 ? c1 : c2;
+  return m > 0.0 ? m : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mesh-cell set-up (mfs.py:1025-1048): exact 4-point homography by 8x8 Gaussian elimination with
+// partial pivoting (operation order fixed, identical to oracle/spec.py solve8_partial_pivot).
+// ---------------------------------------------------------------------------------------------
+MF_HD void homography_4pt(const double* src /*[8] x0,y0,..*/, const double* dst, double* Hout /*[9]*/) {
+  double A[8][9];
+  for (int i = 0; i < 4; ++i) {
+    const double x = src[2 * i], y = src[2 * i + 1], X = dst[2 * i], Y = dst[2 * i + 1];
+    double* r0 = A[2 * i];
+    double* r1 = A[2 * i + 1];
+    r0[0] = x; r0[1] = y; r0[2] = 1.0; r0[3] = 0.0; r0[4] = 0.0; r0[5] = 0.0;
+    r0[6] = -MF_MUL(x, X); r0[7] = -MF_MUL(y, X); r0[8] = X;
+    r1[0] = 0.0; r1[1] = 0.0; r1[2] = 0.0; r1[3] = x; r1[4] = y; r1[5] = 1.0;
+    r1[6] = -MF_MUL(x, Y); r1[7] = -MF_MUL(y, Y); r1[8] = Y;
+  }
+  for (int k = 0; k < 8; ++k) {
+    int piv = k;
+    double best = fabs(A[k][k]);
+    for (int i = k + 1; i < 8; ++i) {
+      const double v = fabs(A[i][k]);
+      if (v > best) { best = v; piv = i; }
+    }
+    if (piv != k) {
+      for (int j = 0; j < 9; ++j) { const double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
+    }
+    for (int i = k + 1; i < 8; ++i) {
+      const double f = MF_DIV(A[i][k], A[k][k]);
+      for (int j = k; j < 9; ++j) A[i][j] = MF_SUB(A[i][j], MF_MUL(f, A[k][j]));
+    }
+  }
+  double h[8];
+  for (int i = 7; i >= 0; --i) {
+    double acc = A[i][8];
+    for (int j = i + 1; j < 8; ++j) acc = MF_SUB(acc, MF_MUL(A[i][j], h[j]));
+    h[i] = MF_DIV(acc, A[i][i]);
+  }
+  for (int i = 0; i < 8; ++i) Hout[i] = h[i];
+  Hout[8] = 1.0;
+}
+
+// closed-form inverse (adjugate / determinant), the order of cv::invert for 3x3 (cv2.warpPerspective)
+MF_HD void inverse3x3(const double* m, double* o) {
+  const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  const double c00 = MF_SUB(MF_MUL(e, i), MF_MUL(f, h));
+  const double c01 = MF_SUB(MF_MUL(d, i), MF_MUL(f, g));
+  const double c02 = MF_SUB(MF_MUL(d, h), MF_MUL(e, g));
+  const double det = MF_ADD(MF_SUB(MF_MUL(a, c00), MF_MUL(b, c01)), MF_MUL(c, c02));
+  const double r = (det != 0.0) ? MF_DIV(1.0, det) : 0.0;
+  o[0] = MF_MUL(c00, r);
+  o[1] = MF_MUL(MF_SUB(MF_MUL(c, h), MF_MUL(b, i)), r);
+  o[2] = MF_MUL(MF_SUB(MF_MUL(b, f), MF_MUL(c, e)), r);
+  o[3] = MF_MUL(MF_SUB(MF_MUL(f, g), MF_MUL(d, i)), r);
+  o[4] = MF_MUL(MF_SUB(MF_MUL(a, i), MF_MUL(c, g)), r);
+  o[5] = MF_MUL(MF_SUB(MF_MUL(c, d), MF_MUL(a, f)), r);
+  o[6] = MF_MUL(c02, r);
+  o[7] = MF_MUL(MF_SUB(MF_MUL(b, g), MF_MUL(a, h)), r);
+  o[8] = MF_MUL(MF_SUB(MF_MUL(a, e), MF_MUL(b, d)), r);
+}
+
+// One mesh cell of one frame, as the warp kernel consumes it.
+struct Cell {
+  double Hsu[8];   // stabilized -> unstabilized homography (h22 == 1), gives the remap coordinates
+  double Mi[9];    // inverse of the unstabilized -> stabilized homography, decides membership
+  int lo_x, hi_x, lo_y, hi_y;   // membership bounds on the 1/32-px source coordinate (inclusive)
+  int bx0, by0, bx1, by1;       // conservative support box in the output frame (inclusive); bx0 > bx1: empty
+};
+
+// rest: 4 corners TL,TR,BL,BR of the rest cell (integer valued), stab: the stabilized corners already
+// rounded to float32 (cv2.findHomography converts its input to float32).
+MF_HD void cell_setup(const double* rest, const double* stab, int W, int H, Cell& out) {
+  double Hus[9], Hsu[9];
+  homography_4pt(rest, stab, Hus);
+  homography_4pt(stab, rest, Hsu);
+  for (int i = 0; i < 8; ++i) out.Hsu[i] = Hsu[i];
+  inverse3x3(Hus, out.Mi);
+  double minx = rest[0], maxx = rest[0], miny = rest[1], maxy = rest[1];
+  for (int i = 1; i < 4; ++i) {
+    minx = rest[2 * i] < minx ? rest[2 * i] : minx;
+    maxx = rest[2 * i] > maxx ? rest[2 * i] : maxx;
+    miny = rest[2 * i + 1] < miny ? rest[2 * i + 1] : miny;
+    maxy = rest[2 * i + 1] > maxy ? rest[2 * i + 1] : maxy;
+  }
+  const int L = (int)floor(minx), Rr = (int)ceil(maxx), T = (int)floor(miny), B = (int)ceil(maxy);
+  out.lo_x = 32 * L - 31; out.hi_x = 32 * Rr + 31;
+  out.lo_y = 32 * T - 31; out.hi_y = 32 * B + 31;
+  // Support of the cell in the output frame = image under Hus of the source rectangle grown by one
+  // pixel.  While the projective denominator keeps one sign on the four grown corners that image is
+  // a bounded convex quad; otherwise fall back to "anywhere".
+  const double gx[4] = {(double)L - 1.0, (double)Rr + 1.0, (double)L - 1.0, (double)Rr + 1.0};
+  const double gy[4] = {(double)T - 1.0, (double)T - 1.0, (double)B + 1.0, (double)B + 1.0};
+  bool pos = true, neg = true, finite = true;
+  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+  for (int i = 0; i < 4; ++i) {
+    const double w = gx[i] * Hus[6] + gy[i] * Hus[7] + Hus[8];
+    pos = pos && (w > 1e-9);
+    neg = neg && (w < -1e-9);
+    const double px = (gx[i] * Hus[0] + gy[i] * Hus[1] + Hus[2]) / w;
+    const double py = (gx[i] * Hus[3] + gy[i] * Hus[4] + Hus[5]) / w;
+    finite = finite && (fabs(px) < 1e9) && (fabs(py) < 1e9);
+    x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
+    y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
+  }
+  if ((pos || neg) && finite) {
+    double fx0 = floor(x0) - 2.0, fx1 = ceil(x1) + 2.0, fy0 = floor(y0) - 2.0, fy1 = ceil(y1) + 2.0;
+    fx0 = fx0 < 0.0 ? 0.0 : fx0; fy0 = fy0 < 0.0 ? 0.0 : fy0;
+    fx1 = fx1 > (double)(W - 1) ? (double)(W - 1) : fx1;
+    fy1 = fy1 > (double)(H - 1) ? (double)(H - 1) : fy1;
+    if (fx0 > fx1 || fy0 > fy1) { out.bx0 = 1; out.bx1 = 0; out.by0 = 1; out.by1 = 0; }
+    else { out.bx0 = (int)fx0; out.bx1 = (int)fx1; out.by0 = (int)fy0; out.by1 = (int)fy1; }
+  } else {
+    out.bx0 = 0; out.by0 = 0; out.bx1 = W - 1; out.by1 = H - 1;
+  }
+}
+
+// cv2.warpPerspective(rect mask) != 0 at output pixel (x, y)  (mfs.py:1050-1052)
+MF_HD bool cell_inside(const Cell& c, double x, double y) {
+  double wd = MF_ADD(MF_ADD(MF_MUL(c.Mi[6], x), MF_MUL(c.Mi[7], y)), c.Mi[8]);
+  wd = (wd != 0.0) ? MF_DIV(32.0, wd) : 0.0;
+  const int X = round_sat(MF_MUL(MF_ADD(MF_ADD(MF_MUL(c.Mi[0], x), MF_MUL(c.Mi[1], y)), c.Mi[2]), wd));
+  const int Y = round_sat(MF_MUL(MF_ADD(MF_ADD(MF_MUL(c.Mi[3], x), MF_MUL(c.Mi[4], y)), c.Mi[5]), wd));
+  return X >= c.lo_x && X <= c.hi_x && Y >= c.lo_y && Y <= c.hi_y;
+}
+
+// float32 remap coordinates of output pixel (x, y) through the cell (mfs.py:1054)
+MF_HD void cell_map(const Cell& c, double x, double y, float& mx, float& my) {
+  double w = MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[6]), MF_MUL(y, c.Hsu[7])), 1.0);
+  w = (fabs(w) > 2.220446049250313e-16) ? MF_DIV(1.0, w) : 0.0;
+  mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[0]), MF_MUL(y, c.Hsu[1])), c.Hsu[2]), w);
+  my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[3]), MF_MUL(y, c.Hsu[4])), c.Hsu[5]), w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv2.remap 8UC3 INTER_LINEAR BORDER_CONSTANT (mfs.py:1063-1069)
+// ---------------------------------------------------------------------------------------------
+MF_HD void remap_coords(float mx, float my, int& ix, int& iy, int& ax, int& ay) {
+  const int sx = round_sat_f(MF_FMUL(mx, 32.0f));
+  const int sy = round_sat_f(MF_FMUL(my, 32.0f));
+  ix = sx >> 5; iy = sy >> 5; ax = sx & 31; ay = sy & 31;
+}
+
+MF_HD int blend4(int p00, int p01, int p10, int p11, int ax, int ay) {
+  return (p00 * (32 - ax) * (32 - ay) + p01 * ax * (32 - ay) + p10 * (32 - ax) * ay + p11 * ax * ay + 512) >> 10;
+}
+
+// Slow-but-general pixel fetch with the constant border.
+MF_HD void remap_pixel(const uint8_t* src, int W, int H, int ix, int iy, int ax, int ay,
+                       int bb, int bg, int br, uint8_t* out3) {
+  const int bord[3] = {bb, bg, br};
+  const bool x0ok = ix >= 0 && ix < W, x1ok = ix + 1 >= 0 && ix + 1 < W;
+  const bool y0ok = iy >= 0 && iy < H, y1ok = iy + 1 >= 0 && iy + 1 < H;
+  const uint8_t* r0 = src + (size_t)(y0ok ? iy : 0) * W * 3;
+  const uint8_t* r1 = src + (size_t)(y1ok ? iy + 1 : 0) * W * 3;
+  const int xa = x0ok ? ix : 0, xb = x1ok ? ix + 1 : 0;
+  for (int ch = 0; ch < 3; ++ch) {
+    const int p00 = (x0ok && y0ok) ? r0[3 * xa + ch] : bord[ch];
+    const int p01 = (x1ok && y0ok) ? r0[3 * xb + ch] : bord[ch];
+    const int p10 = (x0ok && y1ok) ? r1[3 * xa + ch] : bord[ch];
+    const int p11 = (x1ok && y1ok) ? r1[3 * xb + ch] : bord[ch];
+    out3[ch] = (uint8_t)blend4(p00, p01, p10, p11, ax, ay);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv2.resize 8UC3 INTER_LINEAR, 11-bit fixed point (mfs.py:1150-1155)
+// One axis: source index pair and the two integer weights of destination index d.
+// clamp_frac = true for the x axis (fraction zeroed at the borders), false for y (rows clipped only).
+// ---------------------------------------------------------------------------------------------
+MF_HD void resize_coef(int d, int src_len, int dst_len, bool is_x, int& i0, int& i1, int& w0, int& w1) {
+  const double scale = MF_DIV((double)src_len, (double)dst_len);
+  float f = (float)MF_SUB(MF_MUL(MF_ADD((double)d, 0.5), scale), 0.5);
+  int s = (int)floorf(f);
+  f = MF_FSUB(f, (float)s);
+  if (is_x) {
+    if (s < 0) { s = 0; f = 0.0f; }
+    if (s >= src_len - 1) { s = src_len - 1; f = 0.0f; }
+    i0 = s;
+    i1 = (s + 1 < src_len) ? s + 1 : src_len - 1;
+  } else {
+    i0 = s < 0 ? 0 : (s > src_len - 1 ? src_len - 1 : s);
+    i1 = s + 1 < 0 ? 0 : (s + 1 > src_len - 1 ? src_len - 1 : s + 1);
+  }
+  w1 = round_sat_f(MF_FMUL(f, 2048.0f));
+  w0 = round_sat_f(MF_FMUL(MF_FSUB(1.0f, f), 2048.0f));
+}
+
+MF_HD int resize_blend(int p00, int p01, int p10, int p11, int a0, int a1, int b0, int b1) {
+  const int s0 = a0 * p00 + a1 * p01;
+  const int s1 = a0 * p10 + a1 * p11;
+  int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+}  // namespace mf

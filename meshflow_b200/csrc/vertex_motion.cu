@@ -1,0 +1,350 @@
+// Vertex-motion estimation on the device (hot-path subsystem 1).
+//
+//   feature_prepare : one thread per tracked candidate.  Applies the keep mask, moves the feature to
+//                     frame coordinates, takes its residual velocity against the pair's global
+//                     homography and writes, for every mesh row, the inclusive column range of the
+//                     vertices inside the feature's ellipse (mfs.py:420-446).
+//   vertex_median   : one CTA per (vertex, frame pair).  Gathers the residuals of the features whose
+//                     range covers the vertex, selects the median of x and of y independently with an
+//                     8-pass radix select on order-preserving 64-bit keys (statistics.median,
+//                     mfs.py:338-353), adds the vertex's global velocity (mfs.py:325, 354-355).
+//   median3x3       : cv2.medianBlur(.,3) on the (R+1)x(C+1) grid, replicated border (mfs.py:359-360).
+//   prefix          : sequential float64 scan over frame pairs (mfs.py:271, 281).
+//
+// Layout in HBM: residuals [N] double2; ranges [(R+1)][N] uint32 (left | right<<16) so that the
+// vertex CTAs of one mesh row stream one contiguous plane; velocities [P][V][2] float32.
+#include "mf_common.cuh"
+#include "mf_math.cuh"
+
+namespace mf {
+
+static constexpr int kMedianThreads = 128;
+static constexpr uint32_t kEmptyRange = 1u;  // left = 1, right = 0
+
+__global__ void __launch_bounds__(256) feature_prepare_kernel(
+    const float* __restrict__ early_xy, const float* __restrict__ late_xy,
+    const int32_t* __restrict__ offset_xy, const uint8_t* __restrict__ keep,
+    const int32_t* __restrict__ pair_start, int64_t N, int P, const double* __restrict__ homographies,
+    int W, int H, int R, int C, int er, int ec, double2* __restrict__ resid,
+    uint32_t* __restrict__ ranges) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double2 rv = make_double2(0.0, 0.0);
+  bool on = keep[i] != 0;
+  FeatureCell fc;
+  fc.top = 1; fc.bot = 0; fc.frow = 0.0; fc.fcol = 0.0;
+  if (on) {
+    // pair of this feature: last p with pair_start[p] <= i
+    int lo = 0, hi = P;  // invariant: pair_start[lo] <= i < pair_start[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)pair_start[mid] <= i) lo = mid; else hi = mid;
+    }
+    const double* Hm = homographies + (size_t)lo * 9;
+    // float32 subframe coordinate + integer subframe offset, in float64 (mfs.py:578)
+    const double ex = (double)early_xy[2 * i] + (double)offset_xy[2 * i];
+    const double ey = (double)early_xy[2 * i + 1] + (double)offset_xy[2 * i + 1];
+    const double lx = (double)late_xy[2 * i] + (double)offset_xy[2 * i];
+    const double ly = (double)late_xy[2 * i + 1] + (double)offset_xy[2 * i + 1];
+    double px, py;
+    persp(Hm, ex, ey, px, py);
+    rv.x = MF_SUB(lx, px);
+    rv.y = MF_SUB(ly, py);
+    fc = feature_cell(ex, ey, W, H, R, C, er);
+  }
+  resid[i] = rv;
+  for (int vr = 0; vr <= R; ++vr) {
+    uint32_t packed = kEmptyRange;
+    if (on && vr >= fc.top && vr <= fc.bot) {
+      int l, r;
+      col_range(fc, vr, C, er, ec, l, r);
+      if (l <= r) packed = (uint32_t)l | ((uint32_t)r << 16);
+    }
+    ranges[(size_t)vr * N + i] = packed;
+  }
+}
+
+// ---- radix select ---------------------------------------------------------------------------
+struct SelectState {
+  unsigned int hist[2][256];
+  unsigned long long prefix[2];
+  unsigned int rank[2];
+  unsigned long long max_less[2];
+  unsigned int count_less[2];
+  unsigned int count;
+};
+
+// Item sources: the compacted shared-memory list, or (when a vertex has more candidates than the
+// list holds) a re-scan of the pair's features.
+struct ListSource {
+  const unsigned long long* kx;
+  const unsigned long long* ky;
+  int n;
+  template <typename F>
+  __device__ __forceinline__ void for_each(F f) const {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f(kx[i], ky[i]);
+  }
+};
+
+struct ScanSource {
+  const uint32_t* row_ranges;  // plane of this vertex row
+  const double2* resid;
+  int beg, end, vc;
+  template <typename F>
+  __device__ __forceinline__ void for_each(F f) const {
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const uint32_t w = row_ranges[i];
+      const int l = (int)(w & 0xffffu), r = (int)(w >> 16);
+      if (l <= vc && vc <= r) {
+        const double2 v = resid[i];
+        f(key_of(v.x), key_of(v.y));
+      }
+    }
+  }
+};
+
+// Finds the keys of rank k (0-based) among n items for both components; for even n also the key of
+// rank k-1.  All threads of the CTA must call it.  Results in st.prefix (rank k) and lo_key.
+template <typename Source>
+__device__ void select_medians(const Source& src, SelectState& st, int n, double& med_x, double& med_y) {
+  const int k = n >> 1;
+  if (threadIdx.x < 2) { st.prefix[threadIdx.x] = 0ull; st.rank[threadIdx.x] = (unsigned)k; }
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&st.hist[0][0])[i] = 0u;
+    __syncthreads();
+    const unsigned long long px = st.prefix[0], py = st.prefix[1];
+    src.for_each([&](unsigned long long kx, unsigned long long ky) {
+      const bool mx = (pass == 0) || ((kx >> (shift + 8)) == (px >> (shift + 8)));
+      const bool my = (pass == 0) || ((ky >> (shift + 8)) == (py >> (shift + 8)));
+      if (mx) atomicAdd(&st.hist[0][(unsigned)(kx >> shift) & 255u], 1u);
+      if (my) atomicAdd(&st.hist[1][(unsigned)(ky >> shift) & 255u], 1u);
+    });
+    __syncthreads();
+    // warp 0 resolves component 0, warp 1 component 1: each lane owns 8 consecutive buckets
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+      const unsigned int* h = st.hist[warp];
+      unsigned int local[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { local[j] = h[lane * 8 + j]; sum += local[j]; }
+      unsigned int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const unsigned int excl = incl - sum;
+      const unsigned int want = st.rank[warp];
+      if (want >= excl && want < incl) {
+        // b = first bucket of this lane whose cumulative count exceeds `want`
+        unsigned int run = excl;
+        int b = 7;
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!found) {
+            if (want < run + local[j]) { b = j; found = true; }
+            else run += local[j];
+          }
+        }
+        st.prefix[warp] |= ((unsigned long long)(lane * 8 + b)) << shift;
+        st.rank[warp] = want - run;
+      }
+    }
+    __syncthreads();
+  }
+  const unsigned long long hx = st.prefix[0], hy = st.prefix[1];
+  double lo_x = value_of(hx), lo_y = value_of(hy);
+  if ((n & 1) == 0) {
+    if (threadIdx.x < 2) { st.max_less[threadIdx.x] = 0ull; st.count_less[threadIdx.x] = 0u; }
+    __syncthreads();
+    unsigned int cx = 0, cy = 0;
+    unsigned long long bx = 0ull, by = 0ull;
+    src.for_each([&](unsigned long long kx, unsigned long long ky) {
+      if (kx < hx) { ++cx; bx = kx > bx ? kx : bx; }
+      if (ky < hy) { ++cy; by = ky > by ? ky : by; }
+    });
+    if (cx) { atomicAdd(&st.count_less[0], cx); atomicMax(&st.max_less[0], bx); }
+    if (cy) { atomicAdd(&st.count_less[1], cy); atomicMax(&st.max_less[1], by); }
+    __syncthreads();
+    if (st.count_less[0] == (unsigned)k) lo_x = value_of(st.max_less[0]);
+    if (st.count_less[1] == (unsigned)k) lo_y = value_of(st.max_less[1]);
+    med_x = MF_DIV(MF_ADD(lo_x, value_of(hx)), 2.0);
+    med_y = MF_DIV(MF_ADD(lo_y, value_of(hy)), 2.0);
+  } else {
+    med_x = lo_x;
+    med_y = lo_y;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMedianThreads) vertex_median_kernel(
+    const double2* __restrict__ resid, const uint32_t* __restrict__ ranges,
+    const int32_t* __restrict__ pair_start, int64_t N, const double* __restrict__ homographies,
+    const float* __restrict__ vertex_xy, int R, int C, int cap, float* __restrict__ vel_raw,
+    int32_t* __restrict__ assign_count) {
+  extern __shared__ unsigned long long s_keys[];  // [2][cap]
+  __shared__ SelectState st;
+  const int v = blockIdx.x, pair = blockIdx.y;
+  const int V = (R + 1) * (C + 1);
+  const int vr = v / (C + 1), vc = v - vr * (C + 1);
+  const int beg = pair_start[pair], end = pair_start[pair + 1];
+  const uint32_t* row_ranges = ranges + (size_t)vr * N;
+  unsigned long long* kx = s_keys;
+  unsigned long long* ky = s_keys + cap;
+  if (threadIdx.x == 0) st.count = 0u;
+  __syncthreads();
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const uint32_t w = row_ranges[i];
+    const int l = (int)(w & 0xffffu), r = (int)(w >> 16);
+    if (l <= vc && vc <= r) {
+      const unsigned int slot = atomicAdd(&st.count, 1u);
+      if (slot < (unsigned)cap) {
+        const double2 rv = resid[i];
+        kx[slot] = key_of(rv.x);
+        ky[slot] = key_of(rv.y);
+      }
+    }
+  }
+  __syncthreads();
+  const int n = (int)st.count;
+  double med_x = 0.0, med_y = 0.0;
+  if (n > 0) {
+    if (n <= cap) {
+      ListSource src{kx, ky, n};
+      select_medians(src, st, n, med_x, med_y);
+    } else {
+      ScanSource src{row_ranges, resid, beg, end, vc};
+      select_medians(src, st, n, med_x, med_y);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const float vx = vertex_xy[2 * v], vy = vertex_xy[2 * v + 1];
+    double gx, gy;
+    persp(homographies + (size_t)pair * 9, (double)vx, (double)vy, gx, gy);
+    const float glob_x = MF_FSUB((float)gx, vx);      // float32 subtraction (mfs.py:325)
+    const float glob_y = MF_FSUB((float)gy, vy);
+    float* out = vel_raw + ((size_t)pair * V + v) * 2;
+    out[0] = (float)MF_ADD((double)glob_x, med_x);    // mfs.py:354
+    out[1] = (float)MF_ADD((double)glob_y, med_y);    // mfs.py:355
+    if (assign_count) assign_count[(size_t)pair * V + v] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256) median3x3_kernel(const float* __restrict__ vel_raw, int P, int R,
+                                                        int C, float* __restrict__ vel_out) {
+  const int V = (R + 1) * (C + 1);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)P * V) return;
+  const int pair = (int)(idx / V), v = (int)(idx - (int64_t)pair * V);
+  const int vr = v / (C + 1), vc = v - vr * (C + 1);
+  const float* g = vel_raw + (size_t)pair * V * 2;
+  float ax[9], ay[9];
+  int q = 0;
+#pragma unroll
+  for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int rr = min(max(vr + dr, 0), R), cc = min(max(vc + dc, 0), C);
+      const float2 t = reinterpret_cast<const float2*>(g)[rr * (C + 1) + cc];
+      ax[q] = t.x; ay[q] = t.y; ++q;
+    }
+  }
+  reinterpret_cast<float2*>(vel_out)[idx] = make_float2(median9(ax), median9(ay));
+}
+
+__global__ void __launch_bounds__(128) prefix_kernel(const float* __restrict__ vel,
+                                                     const double* __restrict__ disp0,
+                                                     double* __restrict__ disp, int P, int64_t n) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double acc = disp0 ? disp0[j] : 0.0;
+  disp[j] = acc;
+  int t = 0;
+  for (; t + 4 <= P; t += 4) {
+    const float a = vel[(size_t)t * n + j], b = vel[(size_t)(t + 1) * n + j];
+    const float c = vel[(size_t)(t + 2) * n + j], d = vel[(size_t)(t + 3) * n + j];
+    acc = MF_ADD(acc, (double)a); disp[(size_t)(t + 1) * n + j] = acc;
+    acc = MF_ADD(acc, (double)b); disp[(size_t)(t + 2) * n + j] = acc;
+    acc = MF_ADD(acc, (double)c); disp[(size_t)(t + 3) * n + j] = acc;
+    acc = MF_ADD(acc, (double)d); disp[(size_t)(t + 4) * n + j] = acc;
+  }
+  for (; t < P; ++t) {
+    acc = MF_ADD(acc, (double)vel[(size_t)t * n + j]);
+    disp[(size_t)(t + 1) * n + j] = acc;
+  }
+}
+
+struct VertexMotionWorkspace {
+  double2* resid;
+  uint32_t* ranges;
+  float* vel_raw;
+};
+
+static bool carve(Carver& cv, int64_t N, int P, int R, int C, VertexMotionWorkspace& w) {
+  const size_t V = (size_t)(R + 1) * (C + 1);
+  const size_t n = (size_t)(N > 0 ? N : 1);
+  w.resid = cv.take<double2>(n);
+  w.ranges = cv.take<uint32_t>(n * (R + 1));
+  w.vel_raw = cv.take<float>((size_t)P * V * 2);
+  return cv.ok();
+}
+
+}  // namespace mf
+
+extern "C" size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int C) {
+  if (N < 0 || P <= 0 || R <= 0 || C <= 0) return 0;
+  mf::Carver cv(nullptr, 0);
+  mf::VertexMotionWorkspace w;
+  mf::carve(cv, N, P, R, C, w);
+  return mf::align_up(cv.used, 256);
+}
+
+extern "C" int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t* offset_xy,
+                                const uint8_t* keep, const int32_t* pair_start, int64_t N, int P,
+                                int max_pair_features, const double* homographies,
+                                const float* vertex_xy, int W, int H, int R, int C, int ellipse_rows,
+                                int ellipse_cols, float* vel_out, int32_t* assign_count_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  MF_REQUIRE(P > 0 && N >= 0, "mf_vertex_motion: need P > 0 and N >= 0 (P=%d, N=%lld)", P, (long long)N);
+  MF_REQUIRE(W > 0 && H > 0 && R > 0 && C > 0, "mf_vertex_motion: bad frame or mesh size");
+  MF_REQUIRE(R < 65535 && C < 65535, "mf_vertex_motion: mesh too large for 16-bit column ranges");
+  MF_REQUIRE(ellipse_rows > 0 && ellipse_cols > 0, "mf_vertex_motion: ellipse sizes must be positive");
+  MF_REQUIRE(N < 2147483647LL, "mf_vertex_motion: at most 2^31-1 features per call");
+  MF_REQUIRE(pair_start && homographies && vertex_xy && vel_out && workspace,
+             "mf_vertex_motion: null pointer");
+  MF_REQUIRE(N == 0 || (early_xy && late_xy && offset_xy && keep), "mf_vertex_motion: null feature array");
+  mf::Carver cv(workspace, workspace_bytes);
+  mf::VertexMotionWorkspace w;
+  if (!mf::carve(cv, N, P, R, C, w))
+    return mf::fail(MF_E_WORKSPACE, "mf_vertex_motion: workspace %zu < %zu bytes", workspace_bytes, cv.used);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = (R + 1) * (C + 1);
+  if (N > 0) {
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    mf::feature_prepare_kernel<<<blocks, 256, 0, st>>>(early_xy, late_xy, offset_xy, keep, pair_start, N,
+                                                       P, homographies, W, H, R, C, ellipse_rows,
+                                                       ellipse_cols, w.resid, w.ranges);
+    if (int e = mf::check_launch("feature_prepare")) return e;
+  }
+  int cap = max_pair_features < 64 ? 64 : max_pair_features;
+  if (cap > 2816) cap = 2816;  // 2 x 2816 x 8 B = 44 KB of dynamic shared memory
+  cap = (cap + 63) / 64 * 64;
+  if (P > 65535) return mf::fail(MF_E_UNSUPPORTED, "mf_vertex_motion: at most 65535 frame pairs per call");
+  mf::vertex_median_kernel<<<dim3((unsigned)V, (unsigned)P), mf::kMedianThreads,
+                             (size_t)cap * 2 * sizeof(unsigned long long), st>>>(
+      w.resid, w.ranges, pair_start, N, homographies, vertex_xy, R, C, cap, w.vel_raw, assign_count_out);
+  if (int e = mf::check_launch("vertex_median")) return e;
+  const int64_t total = (int64_t)P * V;
+  mf::median3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.vel_raw, P, R, C, vel_out);
+  return mf::check_launch("median3x3");
+}
+
+extern "C" int mf_prefix_displacements(const float* vel, const double* disp0, double* disp, int P,
+                                       int64_t n, void* stream) {
+  MF_REQUIRE(P >= 0 && n > 0, "mf_prefix_displacements: bad sizes");
+  MF_REQUIRE(disp && (P == 0 || vel), "mf_prefix_displacements: null pointer");
+  mf::prefix_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(vel, disp0, disp, P, n);
+  return mf::check_launch("prefix");
+}

@@ -1,0 +1,182 @@
+"""Device-resident stages of the stabilization core (torch tensors in, torch tensors out).
+
+Each method is one C-ABI call (``include/meshflow_b200.h``) on the current CUDA stream; PyTorch is
+only the owner of device memory and streams.  Nothing here falls back to the CPU: the module cannot
+be used without ``libmeshflow_b200.so`` and a CUDA device.
+
+Shapes follow the reference (how4rd/meshflow ``meshflowstabilizer.py``, cited as mfs.py:N):
+``u``/``s`` are ``(F, R+1, C+1, 2)`` float64 displacements, frames are ``(F, H, W, 3)`` uint8 BGR.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+@dataclass(frozen=True)
+class MeshSpec:
+    width: int
+    height: int
+    rows: int = 16
+    cols: int = 16
+
+    @property
+    def vertices(self) -> int:
+        return (self.rows + 1) * (self.cols + 1)
+
+
+def vertex_xy(mesh: MeshSpec) -> np.ndarray:
+    """Rest positions of the mesh vertices, (V,2) float32 -- same expression as mfs.py:901-906
+    (Python float: divide, multiply, ceil)."""
+    out = np.empty((mesh.vertices, 2), dtype=np.float32)
+    k = 0
+    for r in range(mesh.rows + 1):
+        for c in range(mesh.cols + 1):
+            out[k, 0] = math.ceil((mesh.width - 1) * (c / mesh.cols))
+            out[k, 1] = math.ceil((mesh.height - 1) * (r / mesh.rows))
+            k += 1
+    return out
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceCore:
+    """The three hot-path subsystems on one GPU."""
+
+    def __init__(self, mesh: MeshSpec, device=None, ellipse_rows=10, ellipse_cols=10,
+                 radius=10, iterations=100, border_bgr=(0, 0, 255)):
+        if not torch.cuda.is_available():
+            raise RuntimeError("meshflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = _cabi.load()
+        self.mesh = mesh
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ellipse_rows, self.ellipse_cols = int(ellipse_rows), int(ellipse_cols)
+        self.radius, self.iterations = int(radius), int(iterations)
+        self.border_bgr = tuple(int(v) for v in border_bgr)
+        self.vertex_xy_host = vertex_xy(mesh)
+        self.vertex_xy = torch.from_numpy(self.vertex_xy_host).to(self.device)
+        self._ws = {}
+
+    # -- scratch --------------------------------------------------------------------------------
+    def _workspace(self, key, nbytes):
+        nbytes = max(int(nbytes), 256)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    # -- (1) vertex motion ------------------------------------------------------------------------
+    def vertex_velocities(self, early_xy, late_xy, offset_xy, keep, pair_start, homographies,
+                          max_pair_features, return_counts=False):
+        """Batched over P pairs.  Feature tensors are the concatenation over pairs; ``pair_start`` is a
+        (P+1,) int32 device tensor.  Returns (P, R+1, C+1, 2) float32 (mfs.py:287-362)."""
+        m = self.mesh
+        P = int(pair_start.numel()) - 1
+        N = int(early_xy.shape[0])
+        vel = torch.empty((P, m.rows + 1, m.cols + 1, 2), dtype=torch.float32, device=self.device)
+        counts = torch.empty((P, m.vertices), dtype=torch.int32, device=self.device) if return_counts else None
+        ws = self._workspace("vm", self.lib.mf_vertex_motion_workspace_bytes(N, P, m.rows, m.cols))
+        _cabi.check(self.lib.mf_vertex_motion(
+            _ptr(early_xy), _ptr(late_xy), _ptr(offset_xy), _ptr(keep), _ptr(pair_start), N, P,
+            int(max_pair_features), _ptr(homographies), _ptr(self.vertex_xy), m.width, m.height, m.rows,
+            m.cols, self.ellipse_rows, self.ellipse_cols, _ptr(vel), _ptr(counts), _ptr(ws), ws.numel(),
+            _stream()))
+        return (vel, counts) if return_counts else vel
+
+    def prefix_displacements(self, vel, disp0=None):
+        """(P, ...) float32 velocities -> (P+1, ...) float64 displacements (mfs.py:271, 281)."""
+        P = int(vel.shape[0])
+        n = int(vel[0].numel()) if P else int(disp0.numel())
+        disp = torch.empty((P + 1,) + tuple(vel.shape[1:]), dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.mf_prefix_displacements(_ptr(vel), _ptr(disp0), _ptr(disp), P, n, _stream()))
+        return disp
+
+    # -- (2) Jacobi -------------------------------------------------------------------------------
+    def stabilized_displacements(self, u, homographies, definition, vertex_range=None, out=None,
+                                 return_lambda=False):
+        """u: (F, R+1, C+1, 2) float64 -> s of the same shape (mfs.py:632-878).  ``vertex_range``
+        (v0, v1) restricts the solve to a vertex shard; the rest of ``out`` is left untouched."""
+        m = self.mesh
+        F = int(u.shape[0])
+        n_sys = int(u[0].numel())
+        s = torch.empty_like(u) if out is None else out
+        v0, v1 = (0, n_sys // 2) if vertex_range is None else vertex_range
+        lam = torch.empty(F, dtype=torch.float64, device=self.device) if return_lambda else None
+        ws = self._workspace("jac", self.lib.mf_jacobi_workspace_bytes(F, n_sys))
+        _cabi.check(self.lib.mf_jacobi_solve(
+            _ptr(u), _ptr(homographies), _ptr(s), F, n_sys, 2 * int(v0), 2 * int(v1), m.width, m.height,
+            self.radius, self.iterations, int(definition), _ptr(lam), _ptr(ws), ws.numel(), _stream()))
+        return (s, lam) if return_lambda else s
+
+    # -- (3) warp + crop --------------------------------------------------------------------------
+    def warp_frames(self, frames, u, s, out=None, return_maps=False):
+        """frames (nf,H,W,3) uint8 + displacements of the same nf frames -> stabilized frames and the
+        per-frame crop edges (nf,4) int32 [left, top, right, bottom] (mfs.py:909-1100)."""
+        m = self.mesh
+        nf = int(frames.shape[0])
+        dst = torch.empty_like(frames) if out is None else out
+        crop = torch.empty((nf, 4), dtype=torch.int32, device=self.device)
+        maps = torch.empty((nf, m.height, m.width, 2), dtype=torch.float32, device=self.device) if return_maps else None
+        ws = self._workspace("warp", self.lib.mf_warp_workspace_bytes(nf, m.width, m.height, m.rows, m.cols))
+        b, g, r = self.border_bgr
+        _cabi.check(self.lib.mf_warp_frames(
+            _ptr(frames), _ptr(u), _ptr(s), _ptr(self.vertex_xy), nf, m.width, m.height, m.rows, m.cols,
+            b, g, r, _ptr(dst), _ptr(crop), _ptr(maps), _ptr(ws), ws.numel(), _stream()))
+        return (dst, crop, maps) if return_maps else (dst, crop)
+
+    def combine_crop(self, per_frame_crop):
+        """(nf,4) per-frame edges -> device int32[4] = [max left, max top, -min right, -min bottom]
+        (mfs.py:1103-1106): encoded so that ONE max-reduction -- and one all_reduce(MAX) across GPUs --
+        combines it."""
+        enc = torch.empty(4, dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.mf_crop_combine(_ptr(per_frame_crop), int(per_frame_crop.shape[0]), _ptr(enc), _stream()))
+        return enc
+
+    @staticmethod
+    def decode_crop(enc):
+        """Encoded device crop -> (left, top, right, bottom) Python ints (synchronises)."""
+        l, t, nr, nb = (int(v) for v in enc.tolist())
+        return (l, t, -nr, -nb)
+
+    def crop_resize_device(self, frames, crop_enc, out=None):
+        """``crop_resize`` with the rectangle taken from device memory (no host round trip)."""
+        m = self.mesh
+        nf = int(frames.shape[0])
+        dst = torch.empty_like(frames) if out is None else out
+        ws = self._workspace("resize", self.lib.mf_crop_resize_workspace_bytes(m.width, m.height))
+        _cabi.check(self.lib.mf_crop_resize_device(_ptr(frames), nf, m.width, m.height, _ptr(crop_enc), _ptr(dst),
+                                                   _ptr(ws), ws.numel(), _stream()))
+        return dst
+
+    def crop_resize(self, frames, crop, out=None):
+        """crop = (left, top, right, bottom) inclusive Python ints (mfs.py:1111-1157)."""
+        m = self.mesh
+        nf = int(frames.shape[0])
+        dst = torch.empty_like(frames) if out is None else out
+        ws = self._workspace("resize", self.lib.mf_crop_resize_workspace_bytes(m.width, m.height))
+        l, t, r, b = (int(v) for v in crop)
+        _cabi.check(self.lib.mf_crop_resize(_ptr(frames), nf, m.width, m.height, l, t, r, b, _ptr(dst),
+                                            _ptr(ws), ws.numel(), _stream()))
+        return dst
+
+    # -- stability score ----------------------------------------------------------------------------
+    def stability_score(self, s):
+        """mfs.py:1216-1259: mean over vertices of the x ratio and of the y ratio, averaged."""
+        F = int(s.shape[0])
+        n_sys = int(s[0].numel())
+        ratio = torch.empty(n_sys, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.mf_stability_ratios(_ptr(s), F, n_sys, _ptr(ratio), _stream()))
+        r = ratio.view(-1, 2)
+        return (r[:, 0].mean() + r[:, 1].mean()) / 2.0

@@ -283,8 +283,10 @@ def cell_setup(rest_xy, delta, R, C):
 
 
 def _rint_sat(v):
-    v = np.where(np.isnan(v), 0.0, v)
-    return np.rint(np.clip(v, INT_MIN, INT_MAX)).astype(np.int64)
+    # cvRound on x86 (cvtsd2si) turns NaN into INT_MIN, which no membership bound contains
+    nan = np.isnan(v)
+    out = np.rint(np.clip(np.where(nan, 0.0, v), INT_MIN, INT_MAX)).astype(np.int64)
+    return np.where(nan, INT_MIN, out)
 
 
 def cell_inside(cells, n, xs, ys):
@@ -308,7 +310,14 @@ def warp_maps(W, H, cells, prune=True):
     ncell = cells["Hsu"].shape[0]
     for n in range(ncell):
         x0, x1, y0, y1 = 0, W - 1, 0, H - 1
+        mild = False
         if prune:
+            # the quad's bounding box only bounds the support while the cell's projective
+            # denominator stays near 1 on the rest rectangle (no fold, no horizon crossing)
+            hus = cells["Hus"][n]
+            wq = cells["src"][n][:, 0] * hus[6] + cells["src"][n][:, 1] * hus[7] + hus[8]
+            mild = bool(np.all(np.isfinite(wq)) and wq.min() > 0.5 and wq.max() < 2.0)
+        if mild:
             q = cells["dst"][n]
             x0 = max(0, int(math.floor(q[:, 0].min())) - 3); x1 = min(W - 1, int(math.ceil(q[:, 0].max())) + 3)
             y0 = max(0, int(math.floor(q[:, 1].min())) - 3); y1 = min(H - 1, int(math.ceil(q[:, 1].max())) + 3)

@@ -1,0 +1,172 @@
+"""GPU parity tests proper: every stage through the C ABI against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact for feature->vertex assignment, masks, crop indices and
+(because the fixed-point OpenCV models are reproduced) pixels and float32 maps; <= 1e-4 relative on
+optimised vertex paths and metrics -- asserted here at 1e-9 since the kernels are float64.
+"""
+import numpy as np
+import pytest
+
+from oracle import spec
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _core(W, H, R=16, C=16, **kw):
+    from meshflow_b200 import DeviceCore, MeshSpec
+    return DeviceCore(MeshSpec(W, H, R, C), **kw)
+
+
+def _dev(a, core):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(core.device)
+
+
+# ----------------------------------------------------------------------------------------------
+# (1) vertex motion
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H,R,C,n,P", [(640, 360, 16, 16, 1800, 5), (1920, 1080, 16, 16, 3000, 3),
+                                         (320, 180, 8, 12, 400, 4), (640, 360, 16, 16, 3, 3),
+                                         (1280, 720, 64, 64, 2500, 2)])
+def test_vertex_motion_matches_oracle(W, H, R, C, n, P):
+    rng = np.random.default_rng(100 + n)
+    tr = synth.synthetic_tracks(rng, P, n, W, H)
+    core = _core(W, H, R, C)
+    vel, counts = core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
+                                         _dev(tr["keep"], core), _dev(tr["pair_start"], core),
+                                         _dev(tr["homographies"].reshape(-1, 9), core), tr["max_pair"],
+                                         return_counts=True)
+    vel = vel.cpu().numpy(); counts = counts.cpu().numpy()
+    for p in range(P):
+        a, b = tr["pair_start"][p], tr["pair_start"][p + 1]
+        k = tr["keep"][a:b].astype(bool)
+        off = tr["offset"][a:b][k].astype(np.float64)
+        e = tr["early"][a:b][k].astype(np.float64) + off
+        l = tr["late"][a:b][k].astype(np.float64) + off
+        ref, member = spec.vertex_velocities(e, l, tr["homographies"][p], W, H, R, C, 10, 10, return_assignment=True)
+        assert np.array_equal(counts[p], member.sum(axis=0)), "feature->vertex assignment differs"
+        assert np.array_equal(vel[p], ref), f"pair {p}: max |d| = {np.abs(vel[p] - ref).max()}"
+
+
+def test_vertex_motion_overflowing_candidate_list():
+    """More candidates per vertex than the shared-memory list holds -> re-scan path, same medians."""
+    W, H, R, C = 640, 360, 4, 4
+    rng = np.random.default_rng(7)
+    tr = synth.synthetic_tracks(rng, 2, 6000, W, H, keep_prob=1.0)
+    core = _core(W, H, R, C)
+    vel = core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
+                                 _dev(tr["keep"], core), _dev(tr["pair_start"], core),
+                                 _dev(tr["homographies"].reshape(-1, 9), core), 64).cpu().numpy()
+    for p in range(2):
+        a, b = tr["pair_start"][p], tr["pair_start"][p + 1]
+        off = tr["offset"][a:b].astype(np.float64)
+        ref = spec.vertex_velocities(tr["early"][a:b].astype(np.float64) + off, tr["late"][a:b].astype(np.float64) + off,
+                                     tr["homographies"][p], W, H, R, C, 10, 10)
+        assert np.array_equal(vel[p], ref)
+
+
+def test_prefix_sum_is_sequential_float64():
+    rng = np.random.default_rng(3)
+    vel = (rng.normal(0, 3, (257, 17, 17, 2)) * 10 ** rng.uniform(-3, 3, (257, 1, 1, 1))).astype(np.float32)
+    core = _core(640, 360)
+    disp = core.prefix_displacements(_dev(vel, core)).cpu().numpy()
+    assert np.array_equal(disp, spec.prefix_displacements(vel))
+
+
+# ----------------------------------------------------------------------------------------------
+# (2) Jacobi
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,R,radius,iters", [(12, 4, 10, 100), (300, 16, 10, 100), (700, 6, 10, 60),
+                                              (1500, 4, 7, 40), (2600, 2, 30, 25), (300, 4, 30, 50)])
+@pytest.mark.parametrize("definition", [0, 1, 2, 3])
+def test_jacobi_matches_oracle(F, R, radius, iters, definition):
+    rng = np.random.default_rng(F + definition)
+    u, homs = synth.synthetic_paths(rng, F, R, R)
+    core = _core(640, 360, R, R, radius=radius, iterations=iters)
+    s, lam = core.stabilized_displacements(_dev(u, core), _dev(homs, core), definition, return_lambda=True)
+    s = s.cpu().numpy(); lam = lam.cpu().numpy()
+    ref = spec.jacobi_banded(u, homs, 640, 360, radius, iters, definition)
+    assert np.allclose(lam, spec.adaptive_lambda(homs, 640, 360, definition), rtol=1e-12, atol=1e-14)
+    scale = np.abs(ref).max()
+    assert np.abs(s - ref).max() <= 1e-9 * scale            # north-star tolerance: 1e-4 relative
+
+
+def test_jacobi_vertex_shard_only_touches_its_range():
+    rng = np.random.default_rng(11)
+    u, homs = synth.synthetic_paths(rng, 100, 8, 8)
+    core = _core(640, 360, 8, 8)
+    full = core.stabilized_displacements(_dev(u, core), _dev(homs, core), 0).cpu().numpy()
+    out = torch.full((100, 9, 9, 2), -7.0, dtype=torch.float64, device=core.device)
+    core.stabilized_displacements(_dev(u, core), _dev(homs, core), 0, vertex_range=(20, 50), out=out)
+    out = out.cpu().numpy().reshape(100, 81, 2)
+    assert np.array_equal(out[:, 20:50], full.reshape(100, 81, 2)[:, 20:50])
+    assert np.all(out[:, :20] == -7.0) and np.all(out[:, 50:] == -7.0)
+
+
+def test_jacobi_rejects_bad_definition():
+    from meshflow_b200._cabi import MeshflowNativeError
+    core = _core(64, 64, 2, 2)
+    u = torch.zeros((4, 3, 3, 2), dtype=torch.float64, device=core.device)
+    homs = torch.eye(3, dtype=torch.float64, device=core.device).repeat(4, 1, 1)
+    with pytest.raises(MeshflowNativeError):
+        core.stabilized_displacements(u, homs, 4)
+
+
+# ----------------------------------------------------------------------------------------------
+# (3) warp + crop
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H,R,C,F,amp", [(320, 180, 8, 8, 3, 2.5), (640, 360, 16, 16, 2, 3.0),
+                                           (333, 217, 6, 9, 2, 2.0), (200, 120, 4, 6, 2, 15.0),
+                                           (1920, 1080, 16, 16, 1, 3.0), (1280, 720, 64, 64, 1, 1.0)])
+def test_warp_matches_oracle(W, H, R, C, F, amp):
+    rng = np.random.default_rng(W + R)
+    frames, u, s = synth.synthetic_warp_inputs(rng, F, W, H, R, C, per_vertex=amp, per_frame=1.2 * amp)
+    core = _core(W, H, R, C, border_bgr=(7, 99, 250))
+    out, crop, maps = core.warp_frames(_dev(frames, core), _dev(u, core), _dev(s, core), return_maps=True)
+    out = out.cpu().numpy(); crop = crop.cpu().numpy(); maps = maps.cpu().numpy()
+    ref_frames, ref_crop, ref_maps, ref_pf = spec.warp_stage(list(frames), u, s, R, C, (7, 99, 250), return_maps=True)
+    for f in range(F):
+        assert np.array_equal(maps[f, :, :, 0], ref_maps[f][0]), f"map_x differs in {(maps[f, :, :, 0] != ref_maps[f][0]).sum()} px"
+        assert np.array_equal(maps[f, :, :, 1], ref_maps[f][1])
+        assert np.array_equal(out[f], ref_frames[f]), f"{(out[f] != ref_frames[f]).sum()} samples differ"
+        assert crop[f].tolist() == ref_pf[f].tolist()
+    enc = core.combine_crop(torch.from_numpy(crop).to(core.device))
+    assert core.decode_crop(enc) == tuple(ref_crop)
+    if ref_crop[0] <= ref_crop[2] and ref_crop[1] <= ref_crop[3]:
+        a = core.crop_resize_device(torch.from_numpy(out).to(core.device), enc).cpu().numpy()
+        b = core.crop_resize(torch.from_numpy(out).to(core.device), ref_crop).cpu().numpy()
+        assert np.array_equal(a, b)
+        assert np.array_equal(a[0], spec.resize_fixed(out[0][ref_crop[1]:ref_crop[3] + 1, ref_crop[0]:ref_crop[2] + 1], W, H))
+
+
+def test_warp_identity_is_a_copy():
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (2, 180, 320, 3), dtype=np.uint8)
+    u = rng.normal(0, 5, (2, 9, 9, 2))
+    core = _core(320, 180, 8, 8)
+    out, crop = core.warp_frames(_dev(frames, core), _dev(u, core), _dev(u, core))
+    assert np.array_equal(out.cpu().numpy(), frames)
+    assert crop.cpu().numpy().tolist() == [[0, 0, 319, 179]] * 2
+
+
+@pytest.mark.parametrize("W,H,crop", [(640, 360, (13, 9, 620, 344)), (1920, 1080, (79, 55, 1850, 1000)),
+                                      (333, 217, (0, 0, 332, 216)), (640, 360, (100, 10, 300, 350))])
+def test_crop_resize_matches_oracle(W, H, crop):
+    rng = np.random.default_rng(W)
+    frames = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    core = _core(W, H)
+    out = core.crop_resize(_dev(frames, core), crop).cpu().numpy()
+    l, t, r, b = crop
+    for f in range(2):
+        assert np.array_equal(out[f], spec.resize_fixed(frames[f][t:b + 1, l:r + 1], W, H))
+
+
+def test_stability_score_matches_oracle():
+    rng = np.random.default_rng(5)
+    u, _ = synth.synthetic_paths(rng, 240, 16, 16)
+    core = _core(640, 360)
+    got = float(core.stability_score(_dev(u, core)).item())
+    from oracle import reference_port as port
+    assert abs(got - port.stability_score(u)) <= 1e-10 * abs(got)
