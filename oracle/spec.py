@@ -248,7 +248,8 @@ def jacobi_banded(u, homs, W, H, radius, iters, definition):
         acc = np.zeros_like(x)
         for kk, wk in zip(k, w):
             lo, hi = max(0, -kk), min(F, F - kk)
-            acc[lo:hi] += wk * x[lo + kk:hi + kk]
+            if hi > lo:                                   # F <= |k|: no frame has this neighbour
+                acc[lo:hi] += wk * x[lo + kk:hi + kk]
         x = (b + (2.0 * lam).reshape(shape) * acc) / diag.reshape(shape)
     return x.reshape(u.shape)
 

@@ -1,0 +1,99 @@
+"""CPU tests of the kernels' per-element arithmetic (meshflow_b200/csrc/mf_math.cuh) driven through the
+test-only host-emulation harness tests/hostemu (same source, g++ -ffp-contract=off) against the oracle.
+The GPU tests cover the kernels' parallel plumbing; these catch arithmetic drift without a GPU."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import spec
+from tests import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "hostemu", "libmf_hostemu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(HERE, "hostemu", "hostemu.cpp")
+    hdr = os.path.join(HERE, "..", "meshflow_b200", "csrc", "mf_math.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "-o", SO, src], check=True)
+    lib = ctypes.CDLL(SO)
+    lib.emu_median9.restype = ctypes.c_float
+    lib.emu_lambda.restype = ctypes.c_double
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("W,H,R,C,er,ec", [(640, 360, 16, 16, 10, 10), (1920, 1080, 16, 16, 10, 10),
+                                           (1280, 720, 64, 64, 10, 10), (640, 360, 8, 12, 6, 9)])
+def test_feature_to_vertex_membership_is_bit_exact(emu, W, H, R, C, er, ec):
+    rng = np.random.default_rng(W + R)
+    n = 4000
+    fx = rng.uniform(-5, W + 5, n); fy = rng.uniform(-5, H + 5, n)
+    fx[:60] = np.arange(60) * W / C / 2; fy[:60] = np.arange(60) * H / R / 2      # exactly on vertex lines
+    top = np.zeros(n, np.int32); bot = np.zeros(n, np.int32)
+    l = np.zeros((n, R + 1), np.int32); r = np.zeros((n, R + 1), np.int32)
+    emu.emu_feature_ranges(P(fx), P(fy), n, W, H, R, C, er, ec, P(top), P(bot), P(l), P(r))
+    _, _, l2, r2 = spec.feature_vertex_ranges(fx, fy, W, H, R, C, er, ec)
+    cols = np.arange(C + 1)
+    m1 = (cols[None, None, :] >= l[:, :, None]) & (cols[None, None, :] <= r[:, :, None])
+    m2 = (cols[None, None, :] >= l2[:, :, None]) & (cols[None, None, :] <= r2[:, :, None])
+    assert np.array_equal(m1, m2)
+
+
+def test_key_transform_preserves_order_and_roundtrips(emu):
+    rng = np.random.default_rng(1)
+    v = np.concatenate([rng.normal(0, 1, 500) * 10.0 ** rng.integers(-300, 300, 500), [0.0, 1e-320, -1e-320]])   # (-0.0 sorts below +0.0: harmless, both are zero)
+    keys = np.zeros(v.size, np.uint64); back = np.zeros(v.size)
+    emu.emu_key_roundtrip(P(v), v.size, P(keys), P(back))
+    assert np.array_equal(back.view(np.uint64), v.view(np.uint64))
+    order = np.argsort(v, kind="stable")
+    assert np.all(np.diff(keys[order].astype(object)) >= 0)
+
+
+def test_median9_matches_numpy(emu):
+    rng = np.random.default_rng(2)
+    for _ in range(3000):
+        v = rng.normal(size=9).astype(np.float32)
+        if rng.random() < 0.3:
+            v[rng.integers(0, 9, 3)] = v[0]
+        assert emu.emu_median9(P(v)) == np.float32(np.median(v))
+
+
+def test_adaptive_lambda_closed_form(emu):
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        Hm = synth.random_homography(rng, 640, 360, rot=0.2, scale=0.1, trans=40.0)
+        for d in range(4):
+            assert abs(emu.emu_lambda(P(Hm), 640, 360, d) - spec.adaptive_lambda(Hm[None], 640, 360, d)[0]) <= 1e-15
+
+
+@pytest.mark.parametrize("W,H,R,C,amp,seed", [(320, 180, 8, 8, 2.5, 1), (200, 120, 4, 6, 15.0, 3), (256, 144, 16, 16, 1.0, 5)])
+def test_warp_arithmetic_matches_spec(emu, W, H, R, C, amp, seed):
+    assert emu.emu_sizeof_cell() == 168
+    rng = np.random.default_rng(seed)
+    frames, u, s = synth.synthetic_warp_inputs(rng, 1, W, H, R, C, per_vertex=amp, per_frame=1.2 * amp)
+    rest = spec.vertex_xy(W, H, R, C)
+    uu = np.ascontiguousarray(u[0].reshape(-1, 2)); ss = np.ascontiguousarray(s[0].reshape(-1, 2))
+    cells = np.zeros(R * C * 168, np.uint8)
+    emu.emu_cell_setup(P(rest), P(uu), P(ss), W, H, R, C, P(cells))
+    dst = np.zeros((H, W, 3), np.uint8); maps = np.zeros((H, W, 2), np.float32); crop = np.zeros(4, np.int32)
+    src = np.ascontiguousarray(frames[0])
+    emu.emu_warp_frame(P(src), P(cells), R * C, W, H, 9, 8, 7, P(dst), P(maps), P(crop), 1)
+    sc = spec.cell_setup(rest, ss - uu, R, C)
+    mx, my, _ = spec.warp_maps(W, H, sc, prune=False)
+    assert np.array_equal(maps[..., 0], mx) and np.array_equal(maps[..., 1], my)
+    assert np.array_equal(dst, spec.remap_fixed(src, mx, my, (9, 8, 7)))
+    assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
+    if crop[0] <= crop[2] and crop[1] <= crop[3]:
+        out = np.zeros_like(dst)
+        l, t, r, b = (int(v) for v in crop)
+        emu.emu_crop_resize(P(dst), W, H, l, t, r, b, P(out))
+        assert np.array_equal(out, spec.resize_fixed(dst[t:b + 1, l:r + 1], W, H))
