@@ -219,7 +219,6 @@ def run_b200(args):
     homs_pairs = packed["homographies"].reshape(-1, 9)
     h_tracks = {k: pin(packed[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
     h_tracks["homographies"] = pin(homs_pairs)
-    max_pair = packed["max_pair"]
     P = len(packed["pair_start"]) - 1          # = F pairs per rank (the look-ahead frame closes the last one)
     last_rank = rank == world - 1
     F_total = F * world
@@ -242,7 +241,7 @@ def run_b200(args):
                 e = ev(); e.record(); marks.append(e)
         mark()
         vel = core.vertex_velocities(tr["early"], tr["late"], tr["offset"], tr["keep"], tr["pair_start"],
-                                     tr["homographies"], max_pair)                      # (P, R+1, C+1, 2) f32
+                                     tr["homographies"], pair_start_host=packed["pair_start"])                      # (P, R+1, C+1, 2) f32
         mark()
         if world > 1:
             allv = torch.empty((world,) + tuple(vel.shape), dtype=vel.dtype, device=dev)

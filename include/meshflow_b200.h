@@ -52,8 +52,11 @@ const char* mf_last_error(void);
  *   offset_xy         : [N,2] int32, top-left corner of the feature's subframe (mfs.py:509, 578)
  *   keep              : [N] uint8, 1 = survives both masks
  *   pair_start        : [P+1] int32, features of pair p are [pair_start[p], pair_start[p+1])
- *   max_pair_features : upper bound of pair_start[p+1]-pair_start[p]; only sizes the shared-memory
- *                       candidate lists (a too-small value costs speed, never correctness)
+ *   pair_start_host   : the same [P+1] array in HOST memory, or NULL.  With it the library knows the
+ *                       largest pair and takes the fast path (one shared-memory sort per pair and
+ *                       component + bit-matrix rank selection per mesh row; needs <= 16384 features
+ *                       per pair and <= 96 mesh columns); without it, or beyond those sizes, the
+ *                       generic per-vertex radix-select path runs.  Both paths give identical results.
  *   homographies      : [P,9] float64, global early->late homography of each pair (mfs.py:524)
  *   vertex_xy         : [V,2] float32 rest positions (mfs.py:881-906)
  *   vel_out           : [P,V,2] float32 vertex velocities after both median filters
@@ -62,8 +65,8 @@ const char* mf_last_error(void);
  * ---------------------------------------------------------------------------------------------- */
 size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int C);
 int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t* offset_xy,
-                     const uint8_t* keep, const int32_t* pair_start, int64_t N, int P,
-                     int max_pair_features,
+                     const uint8_t* keep, const int32_t* pair_start, const int32_t* pair_start_host,
+                     int64_t N, int P,
                      const double* homographies, const float* vertex_xy,
                      int W, int H, int R, int C, int ellipse_rows, int ellipse_cols,
                      float* vel_out, int32_t* assign_count_out,

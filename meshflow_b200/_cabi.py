@@ -28,7 +28,7 @@ _SIGNATURES = {
     "mf_built_for_sm": (c_int, []),
     "mf_last_error": (c_char_p, []),
     "mf_vertex_motion_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
-    "mf_vertex_motion": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+    "mf_vertex_motion": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mf_prefix_displacements": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),

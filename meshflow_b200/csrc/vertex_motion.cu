@@ -232,6 +232,251 @@ __global__ void __launch_bounds__(kMedianThreads) vertex_median_kernel(
   }
 }
 
+// =================================================================================================
+// Fast path: one 64-bit sort per (pair, component) + a bit-matrix selection per (pair, mesh row).
+//
+// The per-vertex candidate lists overlap heavily (every feature belongs to ~70 vertices), so instead
+// of selecting a median per vertex from its own list, the pair's features are sorted ONCE per
+// component; a vertex's median is then the member of rank n/2 in that order.  Membership of a feature
+// in the vertices of one mesh row is a contiguous column range, kept as a bit mask (1 bit per
+// column).  For 32 consecutive features of the sorted order a warp transposes the 32 x 32 bit matrix
+// with five shuffle steps; lane c then holds the membership bits of column c and a popcount advances
+// that column's running rank.
+// =================================================================================================
+static constexpr int kSortMax = 16384;   // features per pair the shared-memory sort holds
+static constexpr int kSelectWarps = 16;
+static constexpr int kChunks = kSelectWarps / 2;
+
+__global__ void __launch_bounds__(256) feature_prepare_masks_kernel(
+    const float* __restrict__ early_xy, const float* __restrict__ late_xy,
+    const int32_t* __restrict__ offset_xy, const uint8_t* __restrict__ keep,
+    const int32_t* __restrict__ pair_start, int64_t N, int P, const double* __restrict__ homographies,
+    int W, int H, int R, int C, int er, int ec, int nw, unsigned long long* __restrict__ keys,
+    uint32_t* __restrict__ masks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double2 rv = make_double2(0.0, 0.0);
+  const bool on = keep[i] != 0;
+  FeatureCell fc;
+  fc.top = 1; fc.bot = 0; fc.frow = 0.0; fc.fcol = 0.0;
+  if (on) {
+    int lo = 0, hi = P;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)pair_start[mid] <= i) lo = mid; else hi = mid;
+    }
+    const double* Hm = homographies + (size_t)lo * 9;
+    const double ex = (double)early_xy[2 * i] + (double)offset_xy[2 * i];
+    const double ey = (double)early_xy[2 * i + 1] + (double)offset_xy[2 * i + 1];
+    const double lx = (double)late_xy[2 * i] + (double)offset_xy[2 * i];
+    const double ly = (double)late_xy[2 * i + 1] + (double)offset_xy[2 * i + 1];
+    double px, py;
+    persp(Hm, ex, ey, px, py);
+    rv.x = MF_SUB(lx, px);
+    rv.y = MF_SUB(ly, py);
+    fc = feature_cell(ex, ey, W, H, R, C, er);
+  }
+  keys[i] = key_of(rv.x);
+  keys[(size_t)N + i] = key_of(rv.y);
+  for (int vr = 0; vr <= R; ++vr) {
+    int l = 1, r = 0;
+    if (on && vr >= fc.top && vr <= fc.bot) col_range(fc, vr, C, er, ec, l, r);
+    for (int w = 0; w < nw; ++w) {
+      const int a = max(l, 32 * w), b = min(r, 32 * w + 31);
+      uint32_t m = 0u;
+      if (a <= b) m = (b - a == 31) ? 0xffffffffu : (((1u << (b - a + 1)) - 1u) << (a - 32 * w));
+      masks[((size_t)vr * nw + w) * N + i] = m;
+    }
+  }
+}
+
+// Sort of one pair's features by one component.  Elements are single 64-bit words
+// (top 48 key bits | 16-bit local index) so a compare-exchange moves one word; the rare elements whose
+// keys agree in the top 48 bits are put in exact order by a final odd-even pass on the full keys.
+__global__ void __launch_bounds__(1024) pair_sort_kernel(const unsigned long long* __restrict__ keys,
+                                                         const int32_t* __restrict__ pair_start, int64_t N,
+                                                         unsigned long long* __restrict__ sorted_keys,
+                                                         uint16_t* __restrict__ perm) {
+  extern __shared__ unsigned long long s_w[];
+  const int pair = blockIdx.x, comp = blockIdx.y;
+  const int beg = pair_start[pair], n = pair_start[pair + 1] - beg;
+  if (n <= 0) return;
+  const unsigned long long* k = keys + (size_t)comp * N + beg;
+  int npad = 64;
+  while (npad < n) npad <<= 1;
+  const int nt = blockDim.x, tid = threadIdx.x;
+  for (int i = tid; i < npad; i += nt)
+    s_w[i] = (i < n) ? ((k[i] & ~0xffffull) | (unsigned long long)i) : ~0ull;
+  __syncthreads();
+  for (int kk = 2; kk <= npad; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (npad >> 1); t += nt) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int q = i | j;
+        const unsigned long long a = s_w[i], b = s_w[q];
+        const bool up = (i & kk) == 0;
+        if ((a > b) == up) { s_w[i] = b; s_w[q] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // exact order inside runs of equal 48-bit prefixes (almost never needed)
+  for (int round = 0; round < n; ++round) {
+    int swapped = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+      for (int t = tid; 2 * t + phase + 1 < n; t += nt) {
+        const int i = 2 * t + phase;
+        const unsigned long long a = s_w[i], b = s_w[i + 1];
+        if ((a >> 16) == (b >> 16)) {
+          if (k[a & 0xffffull] > k[b & 0xffffull]) { s_w[i] = b; s_w[i + 1] = a; swapped = 1; }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(swapped)) break;
+  }
+  for (int i = tid; i < n; i += nt) {
+    const unsigned int idx = (unsigned int)(s_w[i] & 0xffffull);
+    perm[(size_t)comp * N + beg + i] = (uint16_t)idx;
+    sorted_keys[(size_t)comp * N + beg + i] = k[idx];
+  }
+}
+
+__device__ __forceinline__ int nth_set_bit(uint32_t bits, int r) {   // position of the r-th (0-based) set bit
+  for (int q = 0; q < r; ++q) bits &= bits - 1u;
+  return __ffs((int)bits) - 1;
+}
+
+__device__ __forceinline__ uint32_t transpose32(uint32_t v, int lane) {
+  // 32 x 32 bit-matrix transpose across the warp: on return bit i of lane c = bit c of lane i
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const uint32_t m = sft == 16 ? 0x0000ffffu : sft == 8 ? 0x00ff00ffu : sft == 4 ? 0x0f0f0f0fu
+                     : sft == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, v, sft);
+    v = (lane & sft) ? ((v & ~m) | ((o >> sft) & m)) : ((v & m) | ((o & m) << sft));
+  }
+  return v;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kSelectWarps * 32) row_select_kernel(
+    const uint32_t* __restrict__ masks, const unsigned long long* __restrict__ sorted_keys,
+    const uint16_t* __restrict__ perm, const int32_t* __restrict__ pair_start, int64_t N,
+    const double* __restrict__ homographies, const float* __restrict__ vertex_xy, int R, int C, int ncap,
+    float* __restrict__ vel_raw, int32_t* __restrict__ assign_count) {
+  extern __shared__ uint32_t s_mask[];              // [NW][ncap] membership words of this mesh row
+  __shared__ int s_cnt[NW * 32];                    // members per column
+  __shared__ int s_chunk[2][kChunks][NW * 32];      // members per column inside each chunk of the sorted order
+  __shared__ int s_pos[2][2][NW * 32];              // sorted positions of the lower / upper median
+  const int vr = blockIdx.x, pair = blockIdx.y;
+  const int beg = pair_start[pair], n = pair_start[pair + 1] - beg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = (R + 1) * (C + 1);
+  for (int i = tid; i < NW * 32; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int groups = (n + 31) >> 5;
+  {  // phase 0: stage the row's masks, count members per column
+    int c[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) c[w] = 0;
+    for (int g = warp; g < groups; g += kSelectWarps) {
+      const int i = g * 32 + lane;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t m = (i < n) ? masks[((size_t)vr * NW + w) * N + beg + i] : 0u;
+        if (i < n) s_mask[w * ncap + i] = m;
+        c[w] += __popc(transpose32(m, lane));
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if (c[w]) atomicAdd(&s_cnt[w * 32 + lane], c[w]);
+  }
+  __syncthreads();
+  const int comp = warp & 1, chunk = warp >> 1;
+  const int gpc = (groups + kChunks - 1) / kChunks;
+  const int g0 = min(groups, chunk * gpc), g1 = min(groups, g0 + gpc);
+  const uint16_t* pm = perm + (size_t)comp * N + beg;
+  {  // phase 1: members per column inside this warp's chunk of the sorted order
+    int c[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) c[w] = 0;
+    for (int g = g0; g < g1; ++g) {
+      const int j = g * 32 + lane;
+      const int idx = (j < n) ? (int)pm[j] : -1;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t m = (idx >= 0) ? s_mask[w * ncap + idx] : 0u;
+        c[w] += __popc(transpose32(m, lane));
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_chunk[comp][chunk][w * 32 + lane] = c[w];
+  }
+  __syncthreads();
+  {  // phase 2: the chunk that contains a column's median rank(s) locates them
+    int run[NW], klo[NW], khi[NW];
+    bool any = false;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int col = w * 32 + lane;
+      const int ncol = s_cnt[col];
+      int start = 0;
+      for (int q = 0; q < chunk; ++q) start += s_chunk[comp][q][col];
+      const int mine = s_chunk[comp][chunk][col];
+      run[w] = start;
+      khi[w] = ncol >> 1;
+      klo[w] = (ncol & 1) ? khi[w] : khi[w] - 1;
+      if (ncol == 0) { khi[w] = -1; klo[w] = -1; }
+      any = any || (klo[w] >= start && klo[w] < start + mine) || (khi[w] >= start && khi[w] < start + mine);
+    }
+    if (__any_sync(0xffffffffu, any)) {
+      for (int g = g0; g < g1; ++g) {
+        const int j = g * 32 + lane;
+        const int idx = (j < n) ? (int)pm[j] : -1;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const uint32_t m = (idx >= 0) ? s_mask[w * ncap + idx] : 0u;
+          const uint32_t bits = transpose32(m, lane);
+          const int p = __popc(bits);
+          if (klo[w] >= run[w] && klo[w] < run[w] + p)
+            s_pos[comp][0][w * 32 + lane] = g * 32 + nth_set_bit(bits, klo[w] - run[w]);
+          if (khi[w] >= run[w] && khi[w] < run[w] + p)
+            s_pos[comp][1][w * 32 + lane] = g * 32 + nth_set_bit(bits, khi[w] - run[w]);
+          run[w] += p;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // phase 3: medians -> velocities (one thread per column)
+  if (tid <= C) {
+    const int col = tid;
+    const int ncol = s_cnt[col];
+    double med[2] = {0.0, 0.0};
+    if (ncol > 0) {
+#pragma unroll
+      for (int cp = 0; cp < 2; ++cp) {
+        const unsigned long long* sk = sorted_keys + (size_t)cp * N + beg;
+        const double hi = value_of(sk[s_pos[cp][1][col]]);
+        if (ncol & 1) med[cp] = hi;
+        else med[cp] = MF_DIV(MF_ADD(value_of(sk[s_pos[cp][0][col]]), hi), 2.0);
+      }
+    }
+    const int v = vr * (C + 1) + col;
+    const float vx = vertex_xy[2 * v], vy = vertex_xy[2 * v + 1];
+    double gx, gy;
+    persp(homographies + (size_t)pair * 9, (double)vx, (double)vy, gx, gy);
+    const float glob_x = MF_FSUB((float)gx, vx);      // float32 subtraction (mfs.py:325)
+    const float glob_y = MF_FSUB((float)gy, vy);
+    float* out = vel_raw + ((size_t)pair * V + v) * 2;
+    out[0] = (float)MF_ADD((double)glob_x, med[0]);   // mfs.py:354
+    out[1] = (float)MF_ADD((double)glob_y, med[1]);   // mfs.py:355
+    if (assign_count) assign_count[(size_t)pair * V + v] = ncol;
+  }
+}
+
 __global__ void __launch_bounds__(256) median3x3_kernel(const float* __restrict__ vel_raw, int P, int R,
                                                         int C, float* __restrict__ vel_out) {
   const int V = (R + 1) * (C + 1);
@@ -277,21 +522,53 @@ __global__ void __launch_bounds__(128) prefix_kernel(const float* __restrict__ v
 }
 
 struct VertexMotionWorkspace {
-  double2* resid;
-  uint32_t* ranges;
+  double2* resid;                 // fallback path
+  uint32_t* ranges;               // fallback path
   float* vel_raw;
+  unsigned long long* keys;       // fast path: [2][N]
+  unsigned long long* sorted_keys;// fast path: [2][N]
+  uint16_t* perm;                 // fast path: [2][N]
+  uint32_t* masks;                // fast path: [(R+1)*nw][N]
 };
 
+static int mask_words(int C) { return (C + 1 + 31) / 32; }
+
+// Both paths are carved (the caller sizes the workspace before it knows which one runs).
 static bool carve(Carver& cv, int64_t N, int P, int R, int C, VertexMotionWorkspace& w) {
   const size_t V = (size_t)(R + 1) * (C + 1);
   const size_t n = (size_t)(N > 0 ? N : 1);
-  w.resid = cv.take<double2>(n);
-  w.ranges = cv.take<uint32_t>(n * (R + 1));
   w.vel_raw = cv.take<float>((size_t)P * V * 2);
+  w.keys = cv.take<unsigned long long>(2 * n);
+  w.sorted_keys = cv.take<unsigned long long>(2 * n);
+  w.perm = cv.take<uint16_t>(2 * n);
+  const size_t fast = n * (size_t)(R + 1) * mask_words(C);
+  const size_t slow = n * (size_t)(R + 1);
+  w.masks = cv.take<uint32_t>(fast > slow ? fast : slow);
+  w.ranges = w.masks;             // the two paths never run together
+  w.resid = reinterpret_cast<double2*>(w.keys);
   return cv.ok();
 }
 
+template <int NW>
+static int launch_row_select(const VertexMotionWorkspace& w, const int32_t* pair_start, int64_t N, int P,
+                             const double* homographies, const float* vertex_xy, int R, int C, int ncap,
+                             int32_t* assign_count, cudaStream_t st) {
+  const size_t smem = (size_t)NW * ncap * sizeof(uint32_t);
+  auto k = row_select_kernel<NW>;
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(MF_E_LAUNCH, "row_select: shared memory opt-in: %s", cudaGetErrorString(e));
+  }
+  k<<<dim3((unsigned)(R + 1), (unsigned)P), kSelectWarps * 32, smem, st>>>(
+      w.masks, w.sorted_keys, w.perm, pair_start, N, homographies, vertex_xy, R, C, ncap, w.vel_raw, assign_count);
+  return check_launch("row_select");
+}
+
 }  // namespace mf
+
+// Test hook (not part of the public header): 1 forces the generic per-vertex radix-select path.
+static int mf_force_generic_vertex_motion = 0;
+extern "C" void mf_debug_force_generic_vertex_motion(int on) { mf_force_generic_vertex_motion = on; }
 
 extern "C" size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int C) {
   if (N < 0 || P <= 0 || R <= 0 || C <= 0) return 0;
@@ -302,8 +579,9 @@ extern "C" size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int 
 }
 
 extern "C" int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t* offset_xy,
-                                const uint8_t* keep, const int32_t* pair_start, int64_t N, int P,
-                                int max_pair_features, const double* homographies,
+                                const uint8_t* keep, const int32_t* pair_start,
+                                const int32_t* pair_start_host, int64_t N, int P,
+                                const double* homographies,
                                 const float* vertex_xy, int W, int H, int R, int C, int ellipse_rows,
                                 int ellipse_cols, float* vel_out, int32_t* assign_count_out,
                                 void* workspace, size_t workspace_bytes, void* stream) {
@@ -315,27 +593,68 @@ extern "C" int mf_vertex_motion(const float* early_xy, const float* late_xy, con
   MF_REQUIRE(pair_start && homographies && vertex_xy && vel_out && workspace,
              "mf_vertex_motion: null pointer");
   MF_REQUIRE(N == 0 || (early_xy && late_xy && offset_xy && keep), "mf_vertex_motion: null feature array");
+  // the sort / select kernels size their shared memory from the largest pair, so that number must be
+  // exact: it is taken from the caller's HOST copy of pair_start (absent -> generic path)
+  int max_pair_features = -1;
+  if (pair_start_host) {
+    MF_REQUIRE(pair_start_host[0] == 0 && (int64_t)pair_start_host[P] == N,
+               "mf_vertex_motion: pair_start_host must run from 0 to N");
+    max_pair_features = 0;
+    for (int p = 0; p < P; ++p) {
+      const int c = pair_start_host[p + 1] - pair_start_host[p];
+      MF_REQUIRE(c >= 0, "mf_vertex_motion: pair_start_host must be non-decreasing");
+      max_pair_features = c > max_pair_features ? c : max_pair_features;
+    }
+  }
   mf::Carver cv(workspace, workspace_bytes);
   mf::VertexMotionWorkspace w;
   if (!mf::carve(cv, N, P, R, C, w))
     return mf::fail(MF_E_WORKSPACE, "mf_vertex_motion: workspace %zu < %zu bytes", workspace_bytes, cv.used);
   cudaStream_t st = (cudaStream_t)stream;
   const int V = (R + 1) * (C + 1);
-  if (N > 0) {
-    const unsigned blocks = (unsigned)((N + 255) / 256);
-    mf::feature_prepare_kernel<<<blocks, 256, 0, st>>>(early_xy, late_xy, offset_xy, keep, pair_start, N,
-                                                       P, homographies, W, H, R, C, ellipse_rows,
-                                                       ellipse_cols, w.resid, w.ranges);
-    if (int e = mf::check_launch("feature_prepare")) return e;
-  }
-  int cap = max_pair_features < 64 ? 64 : max_pair_features;
-  if (cap > 2816) cap = 2816;  // 2 x 2816 x 8 B = 44 KB of dynamic shared memory
-  cap = (cap + 63) / 64 * 64;
   if (P > 65535) return mf::fail(MF_E_UNSUPPORTED, "mf_vertex_motion: at most 65535 frame pairs per call");
-  mf::vertex_median_kernel<<<dim3((unsigned)V, (unsigned)P), mf::kMedianThreads,
-                             (size_t)cap * 2 * sizeof(unsigned long long), st>>>(
-      w.resid, w.ranges, pair_start, N, homographies, vertex_xy, R, C, cap, w.vel_raw, assign_count_out);
-  if (int e = mf::check_launch("vertex_median")) return e;
+  const int nw = mf::mask_words(C);
+  const bool fast = N > 0 && max_pair_features >= 0 && max_pair_features <= mf::kSortMax && nw <= 3 &&
+                    !mf_force_generic_vertex_motion;
+  if (fast) {
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    mf::feature_prepare_masks_kernel<<<blocks, 256, 0, st>>>(early_xy, late_xy, offset_xy, keep, pair_start, N, P,
+                                                             homographies, W, H, R, C, ellipse_rows, ellipse_cols,
+                                                             nw, w.keys, w.masks);
+    if (int e = mf::check_launch("feature_prepare_masks")) return e;
+    int npad = 64;
+    while (npad < max_pair_features) npad <<= 1;
+    const size_t sort_smem = (size_t)npad * sizeof(unsigned long long);
+    if (sort_smem > 40 * 1024) {
+      cudaError_t ce = cudaFuncSetAttribute(mf::pair_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sort_smem);
+      if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "pair_sort: shared memory opt-in: %s", cudaGetErrorString(ce));
+    }
+    const int sort_threads = npad / 2 < 1024 ? npad / 2 : 1024;
+    mf::pair_sort_kernel<<<dim3((unsigned)P, 2), sort_threads, sort_smem, st>>>(w.keys, pair_start, N, w.sorted_keys,
+                                                                                w.perm);
+    if (int e = mf::check_launch("pair_sort")) return e;
+    const int ncap = (max_pair_features + 31) / 32 * 32;
+    int e = nw == 1 ? mf::launch_row_select<1>(w, pair_start, N, P, homographies, vertex_xy, R, C, ncap, assign_count_out, st)
+          : nw == 2 ? mf::launch_row_select<2>(w, pair_start, N, P, homographies, vertex_xy, R, C, ncap, assign_count_out, st)
+                    : mf::launch_row_select<3>(w, pair_start, N, P, homographies, vertex_xy, R, C, ncap, assign_count_out, st);
+    if (e) return e;
+  } else {
+    if (N > 0) {
+      const unsigned blocks = (unsigned)((N + 255) / 256);
+      mf::feature_prepare_kernel<<<blocks, 256, 0, st>>>(early_xy, late_xy, offset_xy, keep, pair_start, N,
+                                                         P, homographies, W, H, R, C, ellipse_rows,
+                                                         ellipse_cols, w.resid, w.ranges);
+      if (int e = mf::check_launch("feature_prepare")) return e;
+    }
+    int cap = max_pair_features < 0 ? 2048 : (max_pair_features < 64 ? 64 : max_pair_features);
+    if (cap > 2816) cap = 2816;  // 2 x 2816 x 8 B = 44 KB of dynamic shared memory
+    cap = (cap + 63) / 64 * 64;
+    mf::vertex_median_kernel<<<dim3((unsigned)V, (unsigned)P), mf::kMedianThreads,
+                               (size_t)cap * 2 * sizeof(unsigned long long), st>>>(
+        w.resid, w.ranges, pair_start, N, homographies, vertex_xy, R, C, cap, w.vel_raw, assign_count_out);
+    if (int e = mf::check_launch("vertex_median")) return e;
+  }
   const int64_t total = (int64_t)P * V;
   mf::median3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.vel_raw, P, R, C, vel_out);
   return mf::check_launch("median3x3");

@@ -79,18 +79,26 @@ class DeviceCore:
 
     # -- (1) vertex motion ------------------------------------------------------------------------
     def vertex_velocities(self, early_xy, late_xy, offset_xy, keep, pair_start, homographies,
-                          max_pair_features, return_counts=False):
+                          pair_start_host=None, return_counts=False):
         """Batched over P pairs.  Feature tensors are the concatenation over pairs; ``pair_start`` is a
-        (P+1,) int32 device tensor.  Returns (P, R+1, C+1, 2) float32 (mfs.py:287-362)."""
+        (P+1,) int32 device tensor and ``pair_start_host`` the same array on the host (NumPy int32 or a
+        CPU tensor; it lets the library pick the fast path).  Returns (P, R+1, C+1, 2) float32
+        (mfs.py:287-362)."""
         m = self.mesh
         P = int(pair_start.numel()) - 1
         N = int(early_xy.shape[0])
         vel = torch.empty((P, m.rows + 1, m.cols + 1, 2), dtype=torch.float32, device=self.device)
         counts = torch.empty((P, m.vertices), dtype=torch.int32, device=self.device) if return_counts else None
         ws = self._workspace("vm", self.lib.mf_vertex_motion_workspace_bytes(N, P, m.rows, m.cols))
+        host_ptr = None
+        if pair_start_host is not None:
+            if isinstance(pair_start_host, torch.Tensor):
+                pair_start_host = pair_start_host.numpy()
+            pair_start_host = np.ascontiguousarray(pair_start_host, dtype=np.int32)
+            host_ptr = pair_start_host.ctypes.data
         _cabi.check(self.lib.mf_vertex_motion(
-            _ptr(early_xy), _ptr(late_xy), _ptr(offset_xy), _ptr(keep), _ptr(pair_start), N, P,
-            int(max_pair_features), _ptr(homographies), _ptr(self.vertex_xy), m.width, m.height, m.rows,
+            _ptr(early_xy), _ptr(late_xy), _ptr(offset_xy), _ptr(keep), _ptr(pair_start), host_ptr, N, P,
+            _ptr(homographies), _ptr(self.vertex_xy), m.width, m.height, m.rows,
             m.cols, self.ellipse_rows, self.ellipse_cols, _ptr(vel), _ptr(counts), _ptr(ws), ws.numel(),
             _stream()))
         return (vel, counts) if return_counts else vel

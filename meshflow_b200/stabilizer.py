@@ -175,7 +175,8 @@ class MeshFlowStabilizer:
         dev = core.device
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         vel = core.vertex_velocities(to(p["early"]), to(p["late"]), to(p["offset"]), to(p["keep"]),
-                                     to(p["pair_start"]), to(p["homographies"].reshape(-1, 9)), p["max_pair"])
+                                     to(p["pair_start"]), to(p["homographies"].reshape(-1, 9)),
+                                     pair_start_host=p["pair_start"])
         u = core.prefix_displacements(vel)
         return (u, homs, vel) if return_velocities else (u, homs)
 

@@ -10,7 +10,7 @@ dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(core.device)
 for n, keepp in [(3,1.0),(40,1.0),(1800,0.85),(1800,0.0)]:
     rng = np.random.default_rng(1)
     tr = synth.synthetic_tracks(rng, 2, n, W, H, keep_prob=keepp)
-    vel, counts = core.vertex_velocities(dev(tr["early"]), dev(tr["late"]), dev(tr["offset"]), dev(tr["keep"]), dev(tr["pair_start"]), dev(tr["homographies"].reshape(-1,9)), tr["max_pair"], return_counts=True)
+    vel, counts = core.vertex_velocities(dev(tr["early"]), dev(tr["late"]), dev(tr["offset"]), dev(tr["keep"]), dev(tr["pair_start"]), dev(tr["homographies"].reshape(-1,9)), pair_start_host=tr["pair_start"], return_counts=True)
     vel=vel.cpu().numpy(); counts=counts.cpu().numpy()
     for p in range(2):
         a,b = tr["pair_start"][p], tr["pair_start"][p+1]

@@ -70,8 +70,8 @@ def textured_video(rng, F, W, H, jitter=3.0):
     import cv2
     cw, ch = W + 160, H + 120
     canvas = rng.integers(0, 256, (ch, cw, 3), dtype=np.uint8)
-    canvas = cv2.GaussianBlur(canvas, (0, 0), 2.0)
-    n_shapes = max(40, (cw * ch) // 900)
+    canvas = cv2.GaussianBlur(canvas, (0, 0), 3.0)
+    n_shapes = max(40, (cw * ch) // 2500)      # ~3.7k FAST candidates per 1080p pair, like real footage
     for _ in range(n_shapes):
         color = tuple(int(v) for v in rng.integers(0, 256, 3))
         x, y = int(rng.integers(0, cw)), int(rng.integers(0, ch))

@@ -27,16 +27,21 @@ def _dev(a, core):
 # ----------------------------------------------------------------------------------------------
 # (1) vertex motion
 # ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["fast", "generic"])
 @pytest.mark.parametrize("W,H,R,C,n,P", [(640, 360, 16, 16, 1800, 5), (1920, 1080, 16, 16, 3000, 3),
                                          (320, 180, 8, 12, 400, 4), (640, 360, 16, 16, 3, 3),
-                                         (1280, 720, 64, 64, 2500, 2)])
-def test_vertex_motion_matches_oracle(W, H, R, C, n, P):
+                                         (1280, 720, 64, 64, 2500, 2), (1920, 1080, 16, 16, 13000, 2),
+                                         (640, 360, 40, 40, 700, 2)])
+def test_vertex_motion_matches_oracle(W, H, R, C, n, P, path):
+    """fast = sort + bit-matrix selection (needs the host copy of pair_start); generic = per-vertex
+    radix select.  Both must reproduce the oracle's float32 velocities and assignment counts exactly."""
     rng = np.random.default_rng(100 + n)
     tr = synth.synthetic_tracks(rng, P, n, W, H)
     core = _core(W, H, R, C)
     vel, counts = core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
                                          _dev(tr["keep"], core), _dev(tr["pair_start"], core),
-                                         _dev(tr["homographies"].reshape(-1, 9), core), tr["max_pair"],
+                                         _dev(tr["homographies"].reshape(-1, 9), core),
+                                         pair_start_host=tr["pair_start"] if path == "fast" else None,
                                          return_counts=True)
     vel = vel.cpu().numpy(); counts = counts.cpu().numpy()
     for p in range(P):
@@ -50,15 +55,37 @@ def test_vertex_motion_matches_oracle(W, H, R, C, n, P):
         assert np.array_equal(vel[p], ref), f"pair {p}: max |d| = {np.abs(vel[p] - ref).max()}"
 
 
+def test_vertex_motion_with_duplicate_values_and_ties():
+    """Many identical residuals (sort ties, equal 48-bit key prefixes) must still give the exact median."""
+    W, H, R, C = 640, 360, 8, 8
+    rng = np.random.default_rng(21)
+    tr = synth.synthetic_tracks(rng, 2, 900, W, H, keep_prob=1.0)
+    tr["late"] = (tr["early"] + np.round(rng.normal(0, 1.0, tr["early"].shape) * 4) / 4).astype(np.float32)
+    tr["homographies"][:] = np.eye(3)
+    tr["late"][::7] = tr["late"][::7] + np.float32(2.0 ** -18)          # differ only far below the 48-bit prefix
+    core = _core(W, H, R, C)
+    outs = []
+    for host in (tr["pair_start"], None):
+        outs.append(core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
+                                           _dev(tr["keep"], core), _dev(tr["pair_start"], core),
+                                           _dev(tr["homographies"].reshape(-1, 9), core), pair_start_host=host).cpu().numpy())
+    for p in range(2):
+        a, b = tr["pair_start"][p], tr["pair_start"][p + 1]
+        off = tr["offset"][a:b].astype(np.float64)
+        ref = spec.vertex_velocities(tr["early"][a:b].astype(np.float64) + off, tr["late"][a:b].astype(np.float64) + off,
+                                     tr["homographies"][p], W, H, R, C, 10, 10)
+        assert np.array_equal(outs[0][p], ref) and np.array_equal(outs[1][p], ref)
+
+
 def test_vertex_motion_overflowing_candidate_list():
-    """More candidates per vertex than the shared-memory list holds -> re-scan path, same medians."""
+    """More candidates per vertex than the generic path's shared-memory list holds -> re-scan path."""
     W, H, R, C = 640, 360, 4, 4
     rng = np.random.default_rng(7)
     tr = synth.synthetic_tracks(rng, 2, 6000, W, H, keep_prob=1.0)
     core = _core(W, H, R, C)
     vel = core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
                                  _dev(tr["keep"], core), _dev(tr["pair_start"], core),
-                                 _dev(tr["homographies"].reshape(-1, 9), core), 64).cpu().numpy()
+                                 _dev(tr["homographies"].reshape(-1, 9), core), pair_start_host=None).cpu().numpy()
     for p in range(2):
         a, b = tr["pair_start"][p], tr["pair_start"][p + 1]
         off = tr["offset"][a:b].astype(np.float64)
