@@ -11,7 +11,8 @@ import os
 from ctypes import c_int, c_int64, c_size_t, c_void_p, c_char_p
 
 _LIB_NAME = "libmeshflow_b200.so"
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+# MESHFLOW_B200_LIB lets kernel-tuning scripts point at an alternative build of the same library
+_LIB_PATH = os.environ.get("MESHFLOW_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 class MeshflowNativeError(RuntimeError):

@@ -59,12 +59,13 @@ MF_HD int round_sat(double v) {
 }
 
 MF_HD int round_sat_f(float v) {
+#if defined(__CUDA_ARCH__)
+  const int r = __float2int_rn(v);          // saturates at +-2^31; only NaN needs a hand
+  return (v == v) ? r : MF_INT_MIN;
+#else
   if (!(v == v)) return MF_INT_MIN;
   if (v <= -2147483648.0f) return MF_INT_MIN;
   if (v >= 2147483520.0f) return MF_INT_MAX;
-#if defined(__CUDA_ARCH__)
-  return __float2int_rn(v);
-#else
   return (int)nearbyintf(v);
 #endif
 }
@@ -241,12 +242,20 @@ MF_HD void inverse3x3(const double* m, double* o) {
   o[8] = MF_MUL(MF_SUB(MF_MUL(a, e), MF_MUL(b, d)), r);
 }
 
-// One mesh cell of one frame, as the warp kernel consumes it.
-struct Cell {
-  double Hsu[8];   // stabilized -> unstabilized homography (h22 == 1), gives the remap coordinates
-  double Mi[9];    // inverse of the unstabilized -> stabilized homography, decides membership
-  int lo_x, hi_x, lo_y, hi_y;   // membership bounds on the 1/32-px source coordinate (inclusive)
+// One mesh cell of one frame, as the warp kernel consumes it (240 bytes, 16-byte aligned; ordered by
+// how often a pixel needs each part: support box, float32 screen, map, float64 membership).
+struct alignas(16) Cell {
   int bx0, by0, bx1, by1;       // conservative support box in the output frame (inclusive); bx0 > bx1: empty
+  // float32 screening copy of the membership test (decides only when the answer cannot depend on
+  // rounding; the float64 test below stays the authority inside the +-eps band around the bounds)
+  float fm[9];                  // Mi in box-local coordinates, rounded to float32
+  float flo_x, fhi_x, flo_y, fhi_y;   // bounds in source pixels relative to the rest cell's corner
+  float feps;                   // screening margin in source pixels; < 0: never screen this cell
+  float pad_[2];
+  double Hsu[8];                // stabilized -> unstabilized homography (h22 == 1), gives the remap coordinates
+  double Mi[9];                 // inverse of the unstabilized -> stabilized homography, decides membership
+  int lo_x, hi_x, lo_y, hi_y;   // membership bounds on the 1/32-px source coordinate (inclusive)
+  int pad2_[2];
 };
 
 // rest: 4 corners TL,TR,BL,BR of the rest cell (integer valued), stab: the stabilized corners already
@@ -284,13 +293,53 @@ MF_HD void cell_setup(const double* rest, const double* stab, int W, int H, Cell
     x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
     y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
   }
+  // float32 screening parameters are filled in below once the support box is known
+  for (int i = 0; i < 9; ++i) out.fm[i] = 0.0f;
+  out.flo_x = out.flo_y = -31.5f / 32.0f;
+  out.fhi_x = (float)(Rr - L) + 31.5f / 32.0f;
+  out.fhi_y = (float)(B - T) + 31.5f / 32.0f;
+  out.feps = -1.0f;
   if ((pos || neg) && finite) {
     double fx0 = floor(x0) - 2.0, fx1 = ceil(x1) + 2.0, fy0 = floor(y0) - 2.0, fy1 = ceil(y1) + 2.0;
     fx0 = fx0 < 0.0 ? 0.0 : fx0; fy0 = fy0 < 0.0 ? 0.0 : fy0;
     fx1 = fx1 > (double)(W - 1) ? (double)(W - 1) : fx1;
     fy1 = fy1 > (double)(H - 1) ? (double)(H - 1) : fy1;
     if (fx0 > fx1 || fy0 > fy1) { out.bx0 = 1; out.bx1 = 0; out.by0 = 1; out.by1 = 0; }
-    else { out.bx0 = (int)fx0; out.bx1 = (int)fx1; out.by0 = (int)fy0; out.by1 = (int)fy1; }
+    else {
+      out.bx0 = (int)fx0; out.bx1 = (int)fx1; out.by0 = (int)fy0; out.by1 = (int)fy1;
+      // Screening evaluates Mi in coordinates local to the support box (x' = x - bx0, y' = y - by0)
+      // and relative to the rest cell's corner (X' = X - L, Y' = Y - T), so that every float32
+      // magnitude is of the order of the cell size, not of the frame size.  It is allowed while the
+      // denominator keeps one sign and varies by less than 2x over the box.  Margin: 2^-18 of the
+      // magnitudes entering the quotient (>= 16x the worst-case float32 evaluation error).
+      const double* M = out.Mi;
+      const double d0 = M[6] * fx0 + M[7] * fy0 + M[8];
+      const double lm[9] = {M[0] - (double)L * M[6], M[1] - (double)L * M[7],
+                            (M[0] * fx0 + M[1] * fy0 + M[2]) - (double)L * d0,
+                            M[3] - (double)T * M[6], M[4] - (double)T * M[7],
+                            (M[3] * fx0 + M[4] * fy0 + M[5]) - (double)T * d0,
+                            M[6], M[7], d0};
+      const double bw = fx1 - fx0, bh = fy1 - fy0;
+      const double cx[4] = {0.0, bw, 0.0, bw}, cy[4] = {0.0, 0.0, bh, bh};
+      double dmin = 1e300, dmax = 0.0;
+      bool dpos = true, dneg = true;
+      for (int i = 0; i < 4; ++i) {
+        const double d = lm[6] * cx[i] + lm[7] * cy[i] + lm[8];
+        dpos = dpos && d > 0.0; dneg = dneg && d < 0.0;
+        const double a = fabs(d);
+        dmin = a < dmin ? a : dmin; dmax = a > dmax ? a : dmax;
+      }
+      if ((dpos || dneg) && dmin >= 0.5 * dmax && dmin > 0.0) {
+        const double span = 2.0 * ((double)(Rr - L) + (double)(B - T)) + 8.0;     // |X'|, |Y'| that matter
+        const double mag = (fabs(lm[0]) + fabs(lm[3])) * bw + (fabs(lm[1]) + fabs(lm[4])) * bh + fabs(lm[2]) +
+                           fabs(lm[5]) + (fabs(lm[6]) * bw + fabs(lm[7]) * bh + fabs(lm[8])) * span;
+        const double eps = mag / dmin * (1.0 / 262144.0);
+        if (eps < 0.25) {
+          for (int i = 0; i < 9; ++i) out.fm[i] = (float)(lm[i] / d0);   // normalised: denominator ~ 1
+          out.feps = (float)eps;
+        }
+      }
+    }
   } else {
     out.bx0 = 0; out.by0 = 0; out.bx1 = W - 1; out.by1 = H - 1;
   }
@@ -305,12 +354,94 @@ MF_HD bool cell_inside(const Cell& c, double x, double y) {
   return X >= c.lo_x && X <= c.hi_x && Y >= c.lo_y && Y <= c.hi_y;
 }
 
+// float32 screening of cell_inside: 1 = certainly inside, 0 = certainly outside, -1 = ask cell_inside.
+// x is the pixel column relative to the cell's box (px - bx0); (bx, by, bw) are the row parts
+// fm1*y' + fm2,  fm4*y' + fm5,  fm7*y' + fm8 with y' = py - by0, hoisted by the caller.
+MF_HD int cell_screen(const Cell& c, float x, float bx, float by, float bw) {
+  if (c.feps < 0.0f) return -1;
+#if defined(__CUDA_ARCH__)
+  const float wd = fmaf(c.fm[6], x, bw);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(wd));
+  const float X = fmaf(c.fm[0], x, bx) * r;
+  const float Y = fmaf(c.fm[3], x, by) * r;
+#else
+  const float wd = c.fm[6] * x + bw;
+  const float r = 1.0f / wd;
+  const float X = (c.fm[0] * x + bx) * r;
+  const float Y = (c.fm[3] * x + by) * r;
+#endif
+  const float e = c.feps;
+  const bool in = X > c.flo_x + e && X < c.fhi_x - e && Y > c.flo_y + e && Y < c.fhi_y - e;
+  const bool out = X < c.flo_x - e || X > c.fhi_x + e || Y < c.flo_y - e || Y > c.fhi_y + e;
+  return in ? 1 : (out ? 0 : -1);   // NaN compares false both ways -> -1
+}
+
+// Screening with the outcome split by side, for the end-point argument of the warp kernel: the
+// region "certainly inside" is convex in the output frame (pre-image of a rectangle under a
+// projective map whose denominator keeps its sign), and so is each of the four "certainly beyond
+// this bound" regions; two end points in the same region put the whole segment in it.
+//   bit 0: certainly inside.  bits 1..4: certainly left of lo_x / right of hi_x / above lo_y / below hi_y.
+// Arguments are the cell's float32 parameters as scalars so that callers can keep them in registers.
+MF_HD unsigned screen_sides(float m0, float m3, float m6, float bx, float by, float bw, float x,
+                            float lo_x, float hi_x, float lo_y, float hi_y, float e) {
+#if defined(__CUDA_ARCH__)
+  const float wd = fmaf(m6, x, bw);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(wd));
+  const float X = fmaf(m0, x, bx) * r;
+  const float Y = fmaf(m3, x, by) * r;
+#else
+  const float wd = m6 * x + bw;
+  const float r = 1.0f / wd;
+  const float X = (m0 * x + bx) * r;
+  const float Y = (m3 * x + by) * r;
+#endif
+  unsigned m = 0u;
+  if (X > lo_x + e && X < hi_x - e && Y > lo_y + e && Y < hi_y - e) m |= 1u;
+  if (X < lo_x - e) m |= 2u;
+  if (X > hi_x + e) m |= 4u;
+  if (Y < lo_y - e) m |= 8u;
+  if (Y > hi_y + e) m |= 16u;
+  return m;
+}
+
+MF_HD unsigned cell_screen_sides(const Cell& c, float x, float bx, float by, float bw) {
+  return screen_sides(c.fm[0], c.fm[3], c.fm[6], bx, by, bw, x, c.flo_x, c.fhi_x, c.flo_y, c.fhi_y, c.feps);
+}
+
 // float32 remap coordinates of output pixel (x, y) through the cell (mfs.py:1054)
 MF_HD void cell_map(const Cell& c, double x, double y, float& mx, float& my) {
   double w = MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[6]), MF_MUL(y, c.Hsu[7])), 1.0);
   w = (fabs(w) > 2.220446049250313e-16) ? MF_DIV(1.0, w) : 0.0;
   mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[0]), MF_MUL(y, c.Hsu[1])), c.Hsu[2]), w);
   my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[3]), MF_MUL(y, c.Hsu[4])), c.Hsu[5]), w);
+}
+
+// cell_map with the row products y*Hsu[1], y*Hsu[4], y*Hsu[7] supplied by the caller: every rounding
+// is the one cell_map performs, so the result is bit-identical; 1/w is the correctly rounded
+// reciprocal either way.
+MF_HD void map_row(double h0, double h2, double h3, double h5, double h6, double x, double yh1, double yh4,
+                   double yh7, float& mx, float& my) {
+  double w = MF_ADD(MF_ADD(MF_MUL(x, h6), yh7), 1.0);
+#if defined(__CUDA_ARCH__)
+  w = (fabs(w) > 2.220446049250313e-16) ? __drcp_rn(w) : 0.0;
+#else
+  w = (fabs(w) > 2.220446049250313e-16) ? (1.0 / w) : 0.0;
+#endif
+  mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, h0), yh1), h2), w);
+  my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, h3), yh4), h5), w);
+}
+
+MF_HD void cell_map_row(const Cell& c, double x, double yh1, double yh4, double yh7, float& mx, float& my) {
+  double w = MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[6]), yh7), 1.0);
+#if defined(__CUDA_ARCH__)
+  w = (fabs(w) > 2.220446049250313e-16) ? __drcp_rn(w) : 0.0;
+#else
+  w = (fabs(w) > 2.220446049250313e-16) ? (1.0 / w) : 0.0;
+#endif
+  mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[0]), yh1), c.Hsu[2]), w);
+  my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[3]), yh4), c.Hsu[5]), w);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,27 +7,31 @@
 //                       adjugate inverse used by the membership test, the integer bounds of the rest
 //                       cell and the cell's support box in the output frame; the thread then files
 //                       the cell into the candidate list of every 64x16 output tile its box touches.
-//   warp_kernel       : one CTA per output tile.  Sorts the tile's candidates by descending cell id
-//                       ("the last cell written wins", mfs.py:1060-1061), and per output pixel takes
-//                       the first candidate whose warped rectangle mask is non-zero, evaluates the
-//                       float32 remap coordinate in float64 exactly as the reference, gathers the
-//                       four taps with OpenCV's 1/32-px fixed-point bilinear weights, and folds the
-//                       four crop-edge searches (mfs.py:1075-1098) into warp reductions + atomics.
-//                       Output rows are staged in shared memory and leave as 16-byte vectors.
+//   warp_kernel       : one CTA per 128x8 output tile, one warp per row segment, four adjacent pixels
+//                       per thread.  Sorts the tile's candidates by descending cell id ("the last
+//                       cell written wins", mfs.py:1060-1061); per pixel the first candidate whose
+//                       warped rectangle mask is non-zero wins.  Membership is screened in float32
+//                       (cell-local coordinates, conservative margin) and only decided in float64 --
+//                       with the reference's exact operation order -- inside the margin; the remap
+//                       coordinate is always the reference's float64 sequence.  The four taps use
+//                       OpenCV's 1/32-px fixed-point weights; when the four pixels' footprints are
+//                       adjacent the two source rows are read as aligned 32-bit words.  The four
+//                       crop-edge searches (mfs.py:1075-1098) are warp reductions + atomics.
 //   crop_resize_kernel: cv2.resize of the cropped window back to W x H (mfs.py:1150-1155).
 //
 // HBM layout: frames [nf][H][W][3] uint8 (row pitch 3W, no padding -- BGR24 rows are multiples of 16
-// bytes at every standard resolution); cells [nf][R*C] mf::Cell (168 B); tile lists
+// bytes at every standard resolution); cells [nf][R*C] mf::Cell (240 B); tile lists
 // [nf][tiles][kTileCap] uint16 + counts.
 #include "mf_common.cuh"
 #include "mf_math.cuh"
 
 namespace mf {
 
-static constexpr int kTileW = 64;
-static constexpr int kTileH = 16;
+static constexpr int kTileW = 128;       // warp kernel: one warp = 128 x 1 output pixels, 4 per thread
+static constexpr int kTileH = 8;
+static constexpr int kPix = 4;
 static constexpr int kTileCap = 48;      // candidate cells per tile before the exhaustive fallback
-static constexpr int kWarpThreads = 256; // 64 columns x 4 row phases
+static constexpr int kWarpThreads = 256; // 32 lanes x 8 rows
 
 __global__ void __launch_bounds__(128) cell_setup_kernel(
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
@@ -73,132 +77,228 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
   }
 }
 
-__device__ __forceinline__ bool in_box(const Cell& c, int x, int y) {
-  return x >= c.bx0 && x <= c.bx1 && y >= c.by0 && y <= c.by1;
+// Candidate lists come out of cell_setup_kernel in atomic order; the warp kernel needs them by
+// descending cell id ("the last cell written wins", mfs.py:1060-1061).  Lists are short (typically
+// 4-8 ids): one thread sorts one list in place.
+__global__ void __launch_bounds__(128) tile_sort_kernel(const int* __restrict__ tile_count,
+                                                        uint16_t* __restrict__ tile_list, int64_t ntiles) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int n = tile_count[t];
+  if (n < 2 || n > kTileCap) return;
+  uint16_t* l = tile_list + t * kTileCap;
+  for (int i = 1; i < n; ++i) {
+    const uint16_t v = l[i];
+    int j = i - 1;
+    while (j >= 0 && l[j] < v) { l[j + 1] = l[j]; --j; }
+    l[j + 1] = v;
+  }
 }
 
-template <bool kWriteMaps>
-__global__ void __launch_bounds__(kWarpThreads) warp_kernel(
+// Per-pixel (general) resolution of one output pixel against a list of candidate cells (descending
+// id; list == nullptr: every cell of the frame).  Rare path: group straddles a cell edge, cell not
+// screenable, frame border.
+__device__ __forceinline__ void resolve_pixel(const Cell* __restrict__ fcells, const uint16_t* __restrict__ list,
+                                              int n, int px, int py, float& mx, float& my) {
+  const double x = (double)px, y = (double)py;
+  for (int k = 0; k < n; ++k) {
+    const Cell& c = fcells[list ? (int)__ldg(list + k) : n - 1 - k];
+    const int4 box = __ldg(reinterpret_cast<const int4*>(&c));
+    if (px < box.x || px > box.z || py < box.y || py > box.w) continue;
+    int in = -1;
+    if (c.feps >= 0.0f) {
+      const float fy = (float)(py - box.y);
+      in = cell_screen(c, (float)(px - box.x), fmaf(c.fm[1], fy, c.fm[2]), fmaf(c.fm[4], fy, c.fm[5]),
+                       fmaf(c.fm[7], fy, c.fm[8]));
+    }
+    if (in < 0) in = cell_inside(c, x, y) ? 1 : 0;
+    if (in == 1) { cell_map(c, x, y, mx, my); return; }
+  }
+}
+
+// Four taps of one output pixel, all inside the frame, regrouped per channel.  Each source row
+// contributes 6 bytes (two BGR pixels) at an arbitrary byte phase: they are read as two or three
+// aligned 32-bit words and brought to phase 0 with a funnel shift, then the bytes are regrouped as
+// (p00, p01, p10, p11) per channel.  off0 / off1: byte offsets of the left tap in the two rows.
+__device__ __forceinline__ void gather_taps(const uint8_t* __restrict__ frame, unsigned off0, unsigned off1,
+                                            uint32_t& qb, uint32_t& qg, uint32_t& qr) {
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(frame) + off0;
+  const uintptr_t a1 = reinterpret_cast<uintptr_t>(frame) + off1;
+  const unsigned f0 = (unsigned)(a0 & 3u), f1 = (unsigned)(a1 & 3u);
+  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+  const uint32_t* w1 = reinterpret_cast<const uint32_t*>(a1 & ~(uintptr_t)3);
+  const uint32_t t0 = __ldg(w0), t1 = __ldg(w0 + 1), t2 = (f0 == 3u) ? __ldg(w0 + 2) : 0u;
+  const uint32_t b0 = __ldg(w1), b1 = __ldg(w1 + 1), b2 = (f1 == 3u) ? __ldg(w1 + 2) : 0u;
+  // s0 = bytes 0..3 (B0 G0 R0 B1), s1 = bytes 4..7 (G1 R1 . .) of each row
+  const uint32_t ts0 = __funnelshift_r(t0, t1, f0 * 8u), ts1 = __funnelshift_r(t1, t2, f0 * 8u);
+  const uint32_t bs0 = __funnelshift_r(b0, b1, f1 * 8u), bs1 = __funnelshift_r(b1, b2, f1 * 8u);
+  qb = __byte_perm(ts0, bs0, 0x7430);                                                      // B00 B01 B10 B11
+  const uint32_t tg = __byte_perm(ts0, ts1, 0x5241), bg = __byte_perm(bs0, bs1, 0x5241);   // G0 G1 R0 R1
+  qg = __byte_perm(tg, bg, 0x5410);
+  qr = __byte_perm(tg, bg, 0x7632);
+}
+
+// cv2.remap's fixed-point bilinear blend with two 2-way 16x8-bit dot products per channel
+// against the weight pairs (w00, w01), (w10, w11), w_rc = wy_r * wx_c <= 1024: (sum + 512) >> 10.
+// Byte offsets inside one frame fit 32 bits (8K BGR = 99.5 MB).  Returns the pixel as a BGRx word.
+__device__ __forceinline__ uint32_t blend_interior(const uint8_t* __restrict__ frame, int pitch, int ix, int iy,
+                                                   int ax, int ay) {
+  uint32_t qb, qg, qr;
+  const unsigned off0 = (unsigned)(iy * pitch + ix * 3);
+  gather_taps(frame, off0, off0 + (unsigned)pitch, qb, qg, qr);
+  const uint32_t wxp = (uint32_t)(32 - ax) | ((uint32_t)ax << 16);
+  const uint32_t wa = wxp * (uint32_t)(32 - ay), wb = wxp * (uint32_t)ay;
+  const uint32_t vb = __dp2a_hi(wb, qb, __dp2a_lo(wa, qb, 512u)) >> 10;
+  const uint32_t vg = __dp2a_hi(wb, qg, __dp2a_lo(wa, qg, 512u)) >> 10;
+  const uint32_t vr = __dp2a_hi(wb, qr, __dp2a_lo(wa, qr, 512u)) >> 10;
+  return vb | (vg << 8) | (vr << 16);
+}
+
+__device__ __forceinline__ void store_bgr4(uint8_t* dst, const uint32_t (&o)[kPix], int npx, bool aligned) {
+  if (npx == kPix && aligned) {     // 4 BGRx words -> 12 contiguous bytes
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    __stcs(d32 + 0, (o[0] & 0x00ffffffu) | (o[1] << 24));
+    __stcs(d32 + 1, ((o[1] >> 8) & 0x0000ffffu) | (o[2] << 16));
+    __stcs(d32 + 2, ((o[2] >> 16) & 0x000000ffu) | (o[3] << 8));
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPix; ++j) {
+      if (j < npx) {
+        dst[3 * j + 0] = (uint8_t)(o[j] & 0xffu);
+        dst[3 * j + 1] = (uint8_t)((o[j] >> 8) & 0xffu);
+        dst[3 * j + 2] = (uint8_t)((o[j] >> 16) & 0xffu);
+      }
+    }
+  }
+}
+
+// kFull: the frame is a whole number of 128 x 8 tiles (true at every standard resolution), so no
+// thread needs an edge predicate.
+#ifndef MF_WARP_MINBLOCKS
+#define MF_WARP_MINBLOCKS 6
+#endif
+// No shared memory, no barriers: the candidates' parameters are read through L1 with warp-uniform
+// (broadcast) 128-bit loads, so the only thing a warp ever waits for is its own data.
+template <bool kWriteMaps, bool kFull>
+__global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
     const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out,
     const Cell* __restrict__ cells, const int* __restrict__ tile_count,
     const uint16_t* __restrict__ tile_list, int32_t* __restrict__ crop_out, float* __restrict__ map_out,
     int W, int H, int ncell, int tiles_x, int tiles_y, int bb, int bg, int br) {
-  __shared__ Cell s_cells[kTileCap];
-  __shared__ int s_ids[kTileCap];
-  __shared__ __align__(16) uint8_t s_out[kTileH][kTileW * 3];
-
   const int f = blockIdx.z;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)blockIdx.y * tiles_x + blockIdx.x;
   const int tid = threadIdx.x;
   const Cell* fcells = cells + (size_t)f * ncell;
-  const int nraw = tile_count[tile];
+  const int nraw = __ldg(tile_count + tile);
   const bool overflow = nraw > kTileCap;
-  const int ncand = overflow ? 0 : nraw;
+  const uint16_t* list = overflow ? nullptr : tile_list + tile * kTileCap;   // sorted by descending id
+  const int ncand = overflow ? ncell : nraw;
 
-  if (!overflow) {
-    // rank sort by descending id, then copy the candidates' parameters as 8-byte words
-    int my_id = -1;
-    if (tid < ncand) { my_id = tile_list[tile * kTileCap + tid]; s_ids[tid] = my_id; }
-    __syncthreads();
-    int rank = 0;
-    if (tid < ncand)
-      for (int j = 0; j < ncand; ++j) rank += (s_ids[j] > my_id) ? 1 : 0;
-    __syncthreads();
-    if (tid < ncand) s_ids[rank] = my_id;
-    __syncthreads();
-    constexpr int kWords = sizeof(Cell) / 8;
-    for (int i = tid; i < ncand * kWords; i += kWarpThreads) {
-      const int ci = i / kWords, wi = i - ci * kWords;
-      reinterpret_cast<unsigned long long*>(&s_cells[ci])[wi] =
-          reinterpret_cast<const unsigned long long*>(&fcells[s_ids[ci]])[wi];
+  // thread -> pixels: warp (wx, wy) covers 32 x 4 pixels, lane = 8 columns-of-4 x 4 rows
+  const int warp = tid >> 5, lane = tid & 31;
+  const int py = y0 + (warp >> 2) * 4 + (lane >> 3);
+  const int px0 = x0 + (warp & 3) * 32 + (lane & 7) * kPix;
+  const bool active = kFull || (py < H && px0 < W);
+  const int npx = kFull ? kPix : (active ? min(kPix, W - px0) : 0);
+  const uint8_t* src = frames_in + (size_t)f * H * W * 3;
+
+  float mx[kPix], my[kPix];
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) { mx[j] = (float)(W + 1); my[j] = (float)(H + 1); }   // mfs.py:983-984
+
+  if (active) {
+    // group decision: the first candidate (descending id) that certainly contains both end pixels
+    // contains the whole group; candidates both end pixels are certainly beyond on one side are skipped
+    const Cell* hit = nullptr;
+    bool general = overflow || npx < kPix;
+    for (int k = 0; k < ncand && hit == nullptr && !general; ++k) {
+      const Cell* c = fcells + __ldg(list + k);
+      const int4 box = __ldg(reinterpret_cast<const int4*>(c));
+      if (py < box.y || py > box.w || px0 > box.z || px0 + kPix - 1 < box.x) continue;
+      const float4* cf = reinterpret_cast<const float4*>(c) + 1;
+      const float4 f3 = __ldg(cf + 3);                 // fhi_y, feps
+      if (f3.y < 0.0f || px0 < box.x || px0 + kPix - 1 > box.z) { general = true; break; }
+      const float4 f0 = __ldg(cf), f1 = __ldg(cf + 1), f2 = __ldg(cf + 2);   // fm0..3 | fm4..7 | fm8 flo_x fhi_x flo_y
+      const float fy = (float)(py - box.y);
+      const float rbx = fmaf(f0.y, fy, f0.z), rby = fmaf(f1.x, fy, f1.y), rbw = fmaf(f1.w, fy, f2.x);
+      const unsigned a = screen_sides(f0.x, f0.w, f1.z, rbx, rby, rbw, (float)(px0 - box.x), f2.y, f2.z, f2.w, f3.x, f3.y);
+      const unsigned b = screen_sides(f0.x, f0.w, f1.z, rbx, rby, rbw, (float)(px0 + kPix - 1 - box.x), f2.y, f2.z,
+                                      f2.w, f3.x, f3.y);
+      if (a & b & 1u) hit = c;
+      else if (!(a & b & 30u)) general = true;
     }
-    __syncthreads();
+    if (general) {
+#pragma unroll
+      for (int j = 0; j < kPix; ++j)
+        if (j < npx) resolve_pixel(fcells, list, ncand, px0 + j, py, mx[j], my[j]);
+    } else if (hit != nullptr) {
+      const double2* hs = reinterpret_cast<const double2*>(hit->Hsu);
+      const double2 h01 = __ldg(hs), h23 = __ldg(hs + 1), h45 = __ldg(hs + 2), h67 = __ldg(hs + 3);
+      const double y = (double)py;
+      const double yh1 = MF_MUL(y, h01.y), yh4 = MF_MUL(y, h45.x), yh7 = MF_MUL(y, h67.y);
+#pragma unroll
+      for (int j = 0; j < kPix; ++j)
+        map_row(h01.x, h23.x, h23.y, h45.y, h67.x, (double)(px0 + j), yh1, yh4, yh7, mx[j], my[j]);
+    }
   }
 
-  const uint8_t* src = frames_in + (size_t)f * H * W * 3;
-  const int lx = tid & (kTileW - 1), ly0 = tid >> 6;
-  const int px = x0 + lx;
   int e_left = -1, e_top = -1, e_right = MF_INT_MAX, e_bottom = MF_INT_MAX;
-
+  if (active) {
+    if (kWriteMaps) {
 #pragma unroll
-  for (int j = 0; j < kTileH / 4; ++j) {
-    const int ly = ly0 + 4 * j;
-    const int py = y0 + ly;
-    if (px < W && py < H) {
-      const double x = (double)px, y = (double)py;
-      float mx = (float)(W + 1), my = (float)(H + 1);          // mfs.py:983-984
-      if (!overflow) {
-        for (int k = 0; k < ncand; ++k) {
-          const Cell& c = s_cells[k];
-          if (in_box(c, px, py) && cell_inside(c, x, y)) { cell_map(c, x, y, mx, my); break; }
-        }
-      } else {
-        for (int id = ncell - 1; id >= 0; --id) {
-          const Cell& c = fcells[id];
-          if (in_box(c, px, py) && cell_inside(c, x, y)) { cell_map(c, x, y, mx, my); break; }
-        }
-      }
-      if (kWriteMaps) {
-        float2* mo = reinterpret_cast<float2*>(map_out) + ((size_t)f * H + py) * W + px;
-        *mo = make_float2(mx, my);
-      }
-      // crop-edge searches on the float32-valued map (mfs.py:1075-1098):  |m - e| < 1
-      if (mx > -1.0f && mx < 1.0f) e_left = max(e_left, px);
-      if (mx > (float)(W - 2) && mx < (float)W) e_right = min(e_right, px);
-      if (my > -1.0f && my < 1.0f) e_top = max(e_top, py);
-      if (my > (float)(H - 2) && my < (float)H) e_bottom = min(e_bottom, py);
-
-      int ix, iy, ax, ay;
-      remap_coords(mx, my, ix, iy, ax, ay);
-      uint8_t* o = &s_out[ly][lx * 3];
-      if (ix >= 0 && ix + 1 < W && iy >= 0 && iy + 1 < H) {
-        const uint8_t* p0 = src + ((size_t)iy * W + ix) * 3;
-        const uint8_t* p1 = p0 + (size_t)W * 3;
-        const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+      for (int j = 0; j < kPix; ++j)
+        if (j < npx) reinterpret_cast<float2*>(map_out)[((size_t)f * H + py) * W + px0 + j] = make_float2(mx[j], my[j]);
+    }
+    // crop edges (mfs.py:1075-1098): |m - e| < 1 on the float32-valued map; cheap group pre-test first
+    const float lo_x = fminf(fminf(mx[0], mx[1]), fminf(mx[2], mx[3])), hi_x = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    const float lo_y = fminf(fminf(my[0], my[1]), fminf(my[2], my[3])), hi_y = fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3]));
+    if (lo_x < 1.0f || hi_x > (float)(W - 2) || lo_y < 1.0f || hi_y > (float)(H - 2)) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const int v = __ldg(p0 + ch) * w00 + __ldg(p0 + 3 + ch) * w01 + __ldg(p1 + ch) * w10 +
-                        __ldg(p1 + 3 + ch) * w11;
-          o[ch] = (uint8_t)((v + 512) >> 10);
+      for (int j = 0; j < kPix; ++j) {
+        if (j < npx) {
+          if (mx[j] > -1.0f && mx[j] < 1.0f) e_left = max(e_left, px0 + j);
+          if (mx[j] > (float)(W - 2) && mx[j] < (float)W) e_right = min(e_right, px0 + j);
+          if (my[j] > -1.0f && my[j] < 1.0f) e_top = max(e_top, py);
+          if (my[j] > (float)(H - 2) && my[j] < (float)H) e_bottom = min(e_bottom, py);
         }
-      } else {
-        remap_pixel(src, W, H, ix, iy, ax, ay, bb, bg, br, o);
       }
     }
+    // 1/32-px source coordinates and the fixed-point blend (mfs.py:1063-1069)
+    const uint32_t border = (uint32_t)bb | ((uint32_t)bg << 8) | ((uint32_t)br << 16);
+    uint32_t o[kPix];
+#pragma unroll
+    for (int j = 0; j < kPix; ++j) {
+      int ix, iy, ax, ay;
+      remap_coords(mx[j], my[j], ix, iy, ax, ay);
+      if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
+        o[j] = blend_interior(src, W * 3, ix, iy, ax, ay);
+      } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {
+        o[j] = border;                       // no tap inside the frame: exactly the border colour
+      } else {
+        uint8_t t3[3];
+        remap_pixel(src, W, H, ix, iy, ax, ay, bb, bg, br, t3);
+        o[j] = (uint32_t)t3[0] | ((uint32_t)t3[1] << 8) | ((uint32_t)t3[2] << 16);
+      }
+    }
+    uint8_t* dst = frames_out + ((size_t)f * H * W + (size_t)py * W + px0) * 3;
+    store_bgr4(dst, o, npx, (W & 3) == 0);
   }
 
   // crop edges: warp reduction, then at most four atomics per warp
   const unsigned full = 0xffffffffu;
-  e_left = __reduce_max_sync(full, e_left);
-  e_top = __reduce_max_sync(full, e_top);
-  e_right = __reduce_min_sync(full, e_right);
-  e_bottom = __reduce_min_sync(full, e_bottom);
-  if ((tid & 31) == 0) {
-    int32_t* cr = crop_out + 4 * f;
-    if (e_left >= 0) atomicMax(cr + 0, e_left);
-    if (e_top >= 0) atomicMax(cr + 1, e_top);
-    if (e_right != MF_INT_MAX) atomicMin(cr + 2, e_right);
-    if (e_bottom != MF_INT_MAX) atomicMin(cr + 3, e_bottom);
-  }
-  __syncthreads();
-
-  uint8_t* dst = frames_out + (size_t)f * H * W * 3;
-  const bool vec_ok = ((W * 3) % 16 == 0) && (x0 + kTileW <= W);
-  if (vec_ok) {
-    constexpr int kVecPerRow = kTileW * 3 / 16;  // 12
-    for (int i = tid; i < kTileH * kVecPerRow; i += kWarpThreads) {
-      const int row = i / kVecPerRow, v = i - row * kVecPerRow;
-      if (y0 + row < H) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&s_out[row][v * 16]);
-        *reinterpret_cast<uint4*>(dst + ((size_t)(y0 + row) * W + x0) * 3 + v * 16) = val;
-      }
-    }
-  } else {
-    const int wpx = min(kTileW, W - x0);
-    for (int i = tid; i < kTileH * wpx * 3; i += kWarpThreads) {
-      const int row = i / (wpx * 3), b = i - row * (wpx * 3);
-      if (y0 + row < H) dst[((size_t)(y0 + row) * W + x0) * 3 + b] = s_out[row][b];
+  const bool any_edge = e_left >= 0 || e_top >= 0 || e_right != MF_INT_MAX || e_bottom != MF_INT_MAX;
+  if (__any_sync(full, any_edge)) {
+    e_left = __reduce_max_sync(full, e_left);
+    e_top = __reduce_max_sync(full, e_top);
+    e_right = __reduce_min_sync(full, e_right);
+    e_bottom = __reduce_min_sync(full, e_bottom);
+    if (lane == 0) {
+      int32_t* cr = crop_out + 4 * f;
+      if (e_left >= 0) atomicMax(cr + 0, e_left);
+      if (e_top >= 0) atomicMax(cr + 1, e_top);
+      if (e_right != MF_INT_MAX) atomicMin(cr + 2, e_right);
+      if (e_bottom != MF_INT_MAX) atomicMin(cr + 3, e_bottom);
     }
   }
 }
@@ -251,54 +351,65 @@ __global__ void __launch_bounds__(128) resize_table_kernel(int W, int H, const i
   }
 }
 
-__global__ void __launch_bounds__(kWarpThreads) crop_resize_kernel(
+// cv2.resize of the crop window back to W x H (mfs.py:1150-1155).  Same thread layout
+// as the warp kernel (4 adjacent output pixels per thread); taps come from gather_taps when the two
+// columns are adjacent and away from the frame's last columns, else byte by byte.
+__global__ void __launch_bounds__(128) crop_resize_kernel(
     const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, int W, int H,
     const int32_t* __restrict__ enc4, const int4* __restrict__ xtab, const int4* __restrict__ ytab) {
-  __shared__ __align__(16) uint8_t s_out[kTileH][kTileW * 3];
   int left, top, right_unused, bottom_unused;
   if (!decode_crop(enc4, W, H, left, top, right_unused, bottom_unused)) return;
   const int f = blockIdx.z;
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  const int tid = threadIdx.x;
-  const int lx = tid & (kTileW - 1), ly0 = tid >> 6;
-  const int px = x0 + lx;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int px0 = blockIdx.x * kTileW + warp * 32 + (lane & 7) * kPix;
+  if (px0 >= W) return;
+  const int npx = min(kPix, W - px0);
   const uint8_t* src = frames_in + (size_t)f * H * W * 3;
-  if (px < W) {
-    const int4 xt = xtab[px];
-    const int c0 = (left + xt.x) * 3, c1 = (left + xt.y) * 3;
+  const int pitch = W * 3;
+  // column taps of this thread's four pixels, shared by both of its rows
+  int c0[kPix], c1[kPix];
+  uint32_t wx[kPix];
+  int a0[kPix], a1[kPix];
 #pragma unroll
-    for (int j = 0; j < kTileH / 4; ++j) {
-      const int ly = ly0 + 4 * j, py = y0 + ly;
-      if (py < H) {
-        const int4 yt = ytab[py];
-        const uint8_t* r0 = src + (size_t)(top + yt.x) * W * 3;
-        const uint8_t* r1 = src + (size_t)(top + yt.y) * W * 3;
+  for (int j = 0; j < kPix; ++j) {
+    const int4 xt = __ldg(xtab + min(px0 + j, W - 1));
+    c0[j] = left + xt.x; c1[j] = left + xt.y; a0[j] = xt.z; a1[j] = xt.w;
+    wx[j] = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int py = blockIdx.y * kTileH + half * 4 + (lane >> 3);
+    if (py >= H) continue;
+    const int4 yt = __ldg(ytab + py);
+    const unsigned row0 = (unsigned)((top + yt.x) * pitch), row1 = (unsigned)((top + yt.y) * pitch);
+    uint32_t o[kPix];
+#pragma unroll
+    for (int j = 0; j < kPix; ++j) {
+      o[j] = 0u;
+      if (j >= npx) continue;
+      uint32_t acc = 0u;
+      if (c1[j] == c0[j] + 1 && c0[j] + 3 < W) {
+        uint32_t q[3];
+        gather_taps(src, row0 + (unsigned)(c0[j] * 3), row1 + (unsigned)(c0[j] * 3), q[0], q[1], q[2]);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          s_out[ly][lx * 3 + ch] = (uint8_t)resize_blend(__ldg(r0 + c0 + ch), __ldg(r0 + c1 + ch),
-                                                        __ldg(r1 + c0 + ch), __ldg(r1 + c1 + ch),
-                                                        xt.z, xt.w, yt.z, yt.w);
+          const int s0 = (int)__dp2a_lo(wx[j], q[ch], 0u), s1 = (int)__dp2a_hi(wx[j], q[ch], 0u);
+          const int v = (((yt.z * (s0 >> 4)) >> 16) + ((yt.w * (s1 >> 4)) >> 16) + 2) >> 2;
+          acc |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
         }
+      } else {
+        const uint8_t* r0 = src + row0;
+        const uint8_t* r1 = src + row1;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          acc |= (uint32_t)resize_blend(__ldg(r0 + c0[j] * 3 + ch), __ldg(r0 + c1[j] * 3 + ch),
+                                        __ldg(r1 + c0[j] * 3 + ch), __ldg(r1 + c1[j] * 3 + ch), a0[j], a1[j],
+                                        yt.z, yt.w) << (8 * ch);
       }
+      o[j] = acc;
     }
-  }
-  __syncthreads();
-  uint8_t* dst = frames_out + (size_t)f * H * W * 3;
-  const bool vec_ok = ((W * 3) % 16 == 0) && (x0 + kTileW <= W);
-  if (vec_ok) {
-    constexpr int kVecPerRow = kTileW * 3 / 16;
-    for (int i = tid; i < kTileH * kVecPerRow; i += kWarpThreads) {
-      const int row = i / kVecPerRow, v = i - row * kVecPerRow;
-      if (y0 + row < H)
-        *reinterpret_cast<uint4*>(dst + ((size_t)(y0 + row) * W + x0) * 3 + v * 16) =
-            *reinterpret_cast<const uint4*>(&s_out[row][v * 16]);
-    }
-  } else {
-    const int wpx = min(kTileW, W - x0);
-    for (int i = tid; i < kTileH * wpx * 3; i += kWarpThreads) {
-      const int row = i / (wpx * 3), b = i - row * (wpx * 3);
-      if (y0 + row < H) dst[((size_t)(y0 + row) * W + x0) * 3 + b] = s_out[row][b];
-    }
+    uint8_t* dst = frames_out + ((size_t)f * H * W + (size_t)py * W + px0) * 3;
+    store_bgr4(dst, o, npx, (W & 3) == 0);
   }
 }
 
@@ -348,15 +459,18 @@ extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const d
   mf::cell_setup_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(
       u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, w.tile_count, w.tile_list, crop_out);
   if (int e = mf::check_launch("cell_setup")) return e;
+  const int64_t ntiles = (int64_t)nf * tiles_x * tiles_y;
+  mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
+  if (int e = mf::check_launch("tile_sort")) return e;
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
-  if (map_out)
-    mf::warp_kernel<true><<<grid, mf::kWarpThreads, 0, st>>>(frames_in, frames_out, w.cells, w.tile_count,
-                                                            w.tile_list, crop_out, map_out, W, H, R * C,
-                                                            tiles_x, tiles_y, border_b, border_g, border_r);
-  else
-    mf::warp_kernel<false><<<grid, mf::kWarpThreads, 0, st>>>(frames_in, frames_out, w.cells, w.tile_count,
-                                                             w.tile_list, crop_out, nullptr, W, H, R * C,
-                                                             tiles_x, tiles_y, border_b, border_g, border_r);
+  const bool full = (W % mf::kTileW == 0) && (H % mf::kTileH == 0);
+#define MF_LAUNCH_WARP(MAPS, FULL)                                                                        \
+  mf::warp_kernel<MAPS, FULL><<<grid, mf::kWarpThreads, 0, st>>>(frames_in, frames_out, w.cells, w.tile_count, \
+                                                                w.tile_list, crop_out, map_out, W, H, R * C,  \
+                                                                tiles_x, tiles_y, border_b, border_g, border_r)
+  if (map_out) { if (full) MF_LAUNCH_WARP(true, true); else MF_LAUNCH_WARP(true, false); }
+  else { if (full) MF_LAUNCH_WARP(false, true); else MF_LAUNCH_WARP(false, false); }
+#undef MF_LAUNCH_WARP
   return mf::check_launch("warp");
 }
 
@@ -373,7 +487,7 @@ static int launch_crop_resize(const uint8_t* frames_in, int nf, int W, int H, co
   if (int e = mf::check_launch("resize_table")) return e;
   const dim3 grid((unsigned)((W + mf::kTileW - 1) / mf::kTileW), (unsigned)((H + mf::kTileH - 1) / mf::kTileH),
                   (unsigned)nf);
-  mf::crop_resize_kernel<<<grid, mf::kWarpThreads, 0, st>>>(frames_in, frames_out, W, H, enc4, xtab, ytab);
+  mf::crop_resize_kernel<<<grid, 128, 0, st>>>(frames_in, frames_out, W, H, enc4, xtab, ytab);
   return mf::check_launch("crop_resize");
 }
 

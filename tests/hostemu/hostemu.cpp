@@ -67,8 +67,17 @@ void emu_warp_frame(const uint8_t* src, const mf::Cell* cells, int ncell, int W,
       for (int id = ncell - 1; id >= 0; --id) {
         const mf::Cell& c = cells[id];
         const bool box = px >= c.bx0 && px <= c.bx1 && py >= c.by0 && py <= c.by1;
-        if ((box || !use_box) && mf::cell_inside(c, (double)px, (double)py)) {
-          mf::cell_map(c, (double)px, (double)py, mx, my);
+        if (!(box || !use_box)) continue;
+        // the kernel's order of decisions: float32 screen first, float64 test only when it abstains
+        const float fy = (float)(py - c.by0);
+        int sc = (use_box && c.feps >= 0.0f)
+                     ? mf::cell_screen(c, (float)(px - c.bx0), fmaf(c.fm[1], fy, c.fm[2]), fmaf(c.fm[4], fy, c.fm[5]),
+                                       fmaf(c.fm[7], fy, c.fm[8]))
+                     : -1;
+        if (sc < 0) sc = mf::cell_inside(c, (double)px, (double)py) ? 1 : 0;
+        if (sc == 1) {
+          const double y = (double)py;
+          mf::cell_map_row(c, (double)px, y * c.Hsu[1], y * c.Hsu[4], y * c.Hsu[7], mx, my);
           break;
         }
       }
@@ -82,6 +91,29 @@ void emu_warp_frame(const uint8_t* src, const mf::Cell* cells, int ncell, int W,
       mf::remap_pixel(src, W, H, ix, iy, ax, ay, bb, bg, br, dst + ((size_t)py * W + px) * 3);
     }
   crop4[0] = e_left; crop4[1] = e_top; crop4[2] = e_right; crop4[3] = e_bottom;
+}
+
+// Screening audit over one frame: out[0] = (pixel, cell) pairs examined (pixel inside the cell's box),
+// out[1] = pairs the float32 screen left to the float64 test, out[2] = pairs where a screen decision
+// contradicts the float64 test (must be 0), out[3] = cells that may be screened at all.
+void emu_screen_audit(const mf::Cell* cells, int ncell, int W, int H, long long* out) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (int id = 0; id < ncell; ++id) {
+    const mf::Cell& c = cells[id];
+    if (c.feps >= 0.0f) out[3]++;
+    if (c.bx0 > c.bx1) continue;
+    for (int py = c.by0; py <= c.by1; ++py) {
+      const float fy = (float)(py - c.by0);
+      const float bx = fmaf(c.fm[1], fy, c.fm[2]), by = fmaf(c.fm[4], fy, c.fm[5]), bw = fmaf(c.fm[7], fy, c.fm[8]);
+      for (int px = c.bx0; px <= c.bx1; ++px) {
+        const int sc = mf::cell_screen(c, (float)(px - c.bx0), bx, by, bw);
+        const bool exact = mf::cell_inside(c, (double)px, (double)py);
+        out[0]++;
+        if (sc < 0) out[1]++;
+        else if ((sc == 1) != exact) out[2]++;
+      }
+    }
+  }
 }
 
 // NOTE: the kernel's crop search starts from "no hit"; a hit at column 0 and no hit are the same value.

@@ -75,14 +75,16 @@ def test_adaptive_lambda_closed_form(emu):
             assert abs(emu.emu_lambda(P(Hm), 640, 360, d) - spec.adaptive_lambda(Hm[None], 640, 360, d)[0]) <= 1e-15
 
 
-@pytest.mark.parametrize("W,H,R,C,amp,seed", [(320, 180, 8, 8, 2.5, 1), (200, 120, 4, 6, 15.0, 3), (256, 144, 16, 16, 1.0, 5)])
+@pytest.mark.parametrize("W,H,R,C,amp,seed", [(320, 180, 8, 8, 2.5, 1), (200, 120, 4, 6, 15.0, 3), (256, 144, 16, 16, 1.0, 5),
+                                              (640, 360, 16, 16, 3.0, 7)])
 def test_warp_arithmetic_matches_spec(emu, W, H, R, C, amp, seed):
-    assert emu.emu_sizeof_cell() == 168
+    csz = emu.emu_sizeof_cell()
+    assert csz == 240
     rng = np.random.default_rng(seed)
     frames, u, s = synth.synthetic_warp_inputs(rng, 1, W, H, R, C, per_vertex=amp, per_frame=1.2 * amp)
     rest = spec.vertex_xy(W, H, R, C)
     uu = np.ascontiguousarray(u[0].reshape(-1, 2)); ss = np.ascontiguousarray(s[0].reshape(-1, 2))
-    cells = np.zeros(R * C * 168, np.uint8)
+    cells = np.zeros(R * C * csz, np.uint8)
     emu.emu_cell_setup(P(rest), P(uu), P(ss), W, H, R, C, P(cells))
     dst = np.zeros((H, W, 3), np.uint8); maps = np.zeros((H, W, 2), np.float32); crop = np.zeros(4, np.int32)
     src = np.ascontiguousarray(frames[0])
@@ -92,6 +94,11 @@ def test_warp_arithmetic_matches_spec(emu, W, H, R, C, amp, seed):
     assert np.array_equal(maps[..., 0], mx) and np.array_equal(maps[..., 1], my)
     assert np.array_equal(dst, spec.remap_fixed(src, mx, my, (9, 8, 7)))
     assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
+    audit = np.zeros(4, np.int64)
+    emu.emu_screen_audit(P(cells), R * C, W, H, P(audit))
+    assert audit[2] == 0, "float32 screen contradicted the float64 membership test"
+    if amp < 5:
+        assert audit[3] >= 0.6 * R * C and audit[1] < 0.4 * audit[0]     # mild meshes: mostly screened
     if crop[0] <= crop[2] and crop[1] <= crop[3]:
         out = np.zeros_like(dst)
         l, t, r, b = (int(v) for v in crop)
