@@ -53,6 +53,7 @@ def parse_args():
                     help="real = run the host OpenCV front end on the synthetic video (outside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the streamed (e2e) schedule")
     return ap.parse_args()
 
 
@@ -228,52 +229,24 @@ def run_b200(args):
     d_out = torch.empty_like(d_frames)
     d_stab = torch.empty_like(d_frames)
     ident = torch.eye(3, dtype=torch.float64, device=dev).reshape(1, 9)
-    # vertex shards of the Jacobi solve (equal, padded)
-    vshard = -(-V // world)
-    v0, v1 = min(rank * vshard, V), min((rank + 1) * vshard, V)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_names = ["vertex_motion", "exchange_u", "jacobi", "exchange_s", "warp", "crop_resize", "stability"]
+    stage_names = ["paths (vertex motion + prefix + Jacobi + exchanges)", "warp", "crop_resize", "stability"]
+
+    from meshflow_b200 import StreamedCore, distributed as mfd
+    host_pair_start = packed["pair_start"]
 
     def hot_path(tr, frames_d, out_d, marks=None):
         def mark():
             if marks is not None:
                 e = ev(); e.record(); marks.append(e)
         mark()
-        vel = core.vertex_velocities(tr["early"], tr["late"], tr["offset"], tr["keep"], tr["pair_start"],
-                                     tr["homographies"], pair_start_host=packed["pair_start"])                      # (P, R+1, C+1, 2) f32
-        mark()
-        if world > 1:
-            allv = torch.empty((world,) + tuple(vel.shape), dtype=vel.dtype, device=dev)
-            dist.all_gather_into_tensor(allv, vel)
-            vel_all = allv.reshape((world * P,) + tuple(vel.shape[1:]))[:F_total - 1]
-            allh = torch.empty((world, P, 9), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(allh, tr["homographies"])
-            homs = torch.cat([allh.reshape(-1, 9)[:F_total - 1], ident])
-        else:
-            vel_all = vel[:F - 1]
-            homs = torch.cat([tr["homographies"][:F - 1], ident])
-        u = core.prefix_displacements(vel_all)                                           # (F_total, ...) f64
-        mark()
-        if world > 1:
-            s = torch.empty_like(u)
-            core.stabilized_displacements(u, homs, args.definition, vertex_range=(v0, v1), out=s)
-            mark()
-            shard = torch.zeros((F_total, vshard, 2), dtype=torch.float64, device=dev)
-            shard[:, :v1 - v0] = s.view(F_total, V, 2)[:, v0:v1]
-            alls = torch.empty((world, F_total, vshard, 2), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(alls, shard)
-            s = alls.permute(1, 0, 2, 3).reshape(F_total, world * vshard, 2)[:, :V].reshape(u.shape).contiguous()
-        else:
-            s = core.stabilized_displacements(u, homs, args.definition)
-            mark()
+        u, s, _ = mfd.sharded_paths(core, tr, F, args.definition, pair_start_host=host_pair_start)
         mark()
         lo = rank * F
         _, crop_pf = core.warp_frames(frames_d, u[lo:lo + F], s[lo:lo + F], out=d_stab)
         mark()
-        enc = core.combine_crop(crop_pf)
-        if world > 1:
-            dist.all_reduce(enc, op=dist.ReduceOp.MAX)
+        enc = mfd.reduce_crop(core.combine_crop(crop_pf))
         core.crop_resize_device(d_stab, enc, out=out_d)
         mark()
         score = core.stability_score(s)
@@ -310,12 +283,13 @@ def run_b200(args):
     crop = core.decode_crop(enc)
 
     # ---- end-to-end timing: host buffers in, host buffers out ------------------------------------------
+    streamed = StreamedCore(core, chunk_frames=args.chunk)
+
     def e2e_step():
-        tr = {k: v.to(dev, non_blocking=True) for k, v in h_tracks.items()}
-        fr = h_frames.to(dev, non_blocking=True)
-        enc, score = hot_path(tr, fr, d_out)
-        h_out.copy_(d_out, non_blocking=True)
-        return enc, score.item()           # device -> host read of the step's result
+        # pinned host frames + tracks in, pinned host frames out; copies overlap the kernels
+        enc, u, s = streamed.run(h_frames, h_tracks, h_out, args.definition)
+        score = core.stability_score(s)
+        return enc, score.item()           # device -> host read of the step's result (synchronises)
 
     for _ in range(max(1, args.warmup - 1)):
         e2e_step()
@@ -350,6 +324,7 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     warp_bytes = 6.0 * H * W * F                       # read source once + write stabilized once, per launch
     achieved = warp_bytes / (stage_ms["warp"] / 1e3) / 1e9
+    resize_gbs = warp_bytes / (stage_ms["crop_resize"] / 1e3) / 1e9
     out = {
         "metric": "stabilized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -361,12 +336,13 @@ def run_b200(args):
                    "crop": list(crop), "parallelism": f"frames x{world}, Jacobi vertices x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": 12 * args.steps,
+        "gpu_launches": 14 * args.steps,
         "stages_ms": stage_ms,
         "roofline": {"kernel": "warp_kernel (mf_warp_frames, incl. cell_setup)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": warp_bytes},
+        "crop_resize_gbs": resize_gbs,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -111,6 +111,14 @@ int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s, c
                    uint8_t* frames_out, int32_t* crop_out, float* map_out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pass A of the streamed schedule: the per-frame crop edges of mf_warp_frames WITHOUT touching a
+ * pixel (the remap coordinates depend on the vertex paths only).  With the crop rectangle of the
+ * whole video known up front, warp -> crop/resize can run chunk by chunk while frames are still being
+ * uploaded and results downloaded.  Same crop_out as mf_warp_frames, same workspace size. */
+int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H,
+                        int R, int C, int32_t* crop_out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* Crop rectangle (inclusive) stretched back to W x H -- replaces _crop_frames (mfs.py:1111-1157);
  * cv2.resize INTER_LINEAR 11-bit fixed point. */
 size_t mf_crop_resize_workspace_bytes(int W, int H);

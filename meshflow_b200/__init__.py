@@ -5,8 +5,8 @@ point, same returned tuple); the three data-parallel stages run as hand-written 
 behind the C ABI in ``include/meshflow_b200.h``.  See DESIGN.md.
 """
 from .stabilizer import MeshFlowStabilizer
-from .pipeline import DeviceCore, MeshSpec, vertex_xy
+from .pipeline import DeviceCore, MeshSpec, StreamedCore, vertex_xy
 from . import _cabi, host_features
 
-__all__ = ["MeshFlowStabilizer", "DeviceCore", "MeshSpec", "vertex_xy", "host_features"]
+__all__ = ["MeshFlowStabilizer", "DeviceCore", "MeshSpec", "StreamedCore", "vertex_xy", "host_features"]
 __version__ = "0.1.0"

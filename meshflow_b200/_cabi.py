@@ -40,6 +40,8 @@ _SIGNATURES = {
     "mf_warp_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
+    "mf_warp_crop_bounds": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
     "mf_crop_resize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mf_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                c_void_p, c_size_t, c_void_p]),

@@ -31,6 +31,8 @@ static constexpr int kTileW = 128;       // warp kernel: one warp = 128 x 1 outp
 static constexpr int kTileH = 8;
 static constexpr int kPix = 4;
 static constexpr int kTileCap = 48;      // candidate cells per tile before the exhaustive fallback
+static constexpr int kCountMask = 0xffff; // tile_count: low 16 bits = candidates, bit 16 = has a border cell
+static constexpr int kEdgeFlag = 0x10000;
 static constexpr int kWarpThreads = 256; // 32 lanes x 8 rows
 
 __global__ void __launch_bounds__(128) cell_setup_kernel(
@@ -65,14 +67,20 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
   cell_setup(rest, stab, W, H, cell);
   cells[idx] = cell;
   if (cell.bx0 > cell.bx1) return;
+  // Only cells whose rest rectangle reaches within two pixels of the frame border can produce remap
+  // coordinates that satisfy a crop-edge search (|m - e| < 1, mfs.py:1075-1098): a pixel mapped by
+  // cell (L..Rr, T..B) has map_x in [L-1, Rr+1], map_y in [T-1, B+1].  Tiles are tagged so that the
+  // bounds-only pass can skip everything else.
+  const bool edge_cell = rest[0] <= 2.0 || rest[1] <= 2.0 || rest[6] >= (double)(W - 3) || rest[7] >= (double)(H - 3);
   const int ntiles = tiles_x * tiles_y;
   const int tx0 = cell.bx0 / kTileW, tx1 = cell.bx1 / kTileW;
   const int ty0 = cell.by0 / kTileH, ty1 = cell.by1 / kTileH;
   for (int ty = ty0; ty <= ty1; ++ty) {
     for (int tx = tx0; tx <= tx1; ++tx) {
       const size_t t = (size_t)f * ntiles + (size_t)ty * tiles_x + tx;
-      const int slot = atomicAdd(&tile_count[t], 1);
+      const int slot = atomicAdd(&tile_count[t], 1) & kCountMask;
       if (slot < kTileCap) tile_list[t * kTileCap + slot] = (uint16_t)id;
+      if (edge_cell) atomicOr(&tile_count[t], kEdgeFlag);
     }
   }
 }
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(128) tile_sort_kernel(const int* __restrict__ 
                                                         uint16_t* __restrict__ tile_list, int64_t ntiles) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
-  const int n = tile_count[t];
+  const int n = tile_count[t] & kCountMask;
   if (n < 2 || n > kTileCap) return;
   uint16_t* l = tile_list + t * kTileCap;
   for (int i = 1; i < n; ++i) {
@@ -175,11 +183,14 @@ __device__ __forceinline__ void store_bgr4(uint8_t* dst, const uint32_t (&o)[kPi
 // kFull: the frame is a whole number of 128 x 8 tiles (true at every standard resolution), so no
 // thread needs an edge predicate.
 #ifndef MF_WARP_MINBLOCKS
-#define MF_WARP_MINBLOCKS 6
+#define MF_WARP_MINBLOCKS 8
 #endif
 // No shared memory, no barriers: the candidates' parameters are read through L1 with warp-uniform
 // (broadcast) 128-bit loads, so the only thing a warp ever waits for is its own data.
-template <bool kWriteMaps, bool kFull>
+// kBoundsOnly: evaluate the maps of the tiles that hold a border cell and fold them into the crop-edge
+// searches, touching no pixel (pass A of the streamed schedule: the crop rectangle of the whole video
+// is known before the first frame has been uploaded).
+template <bool kWriteMaps, bool kFull, bool kBoundsOnly>
 __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
     const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out,
     const Cell* __restrict__ cells, const int* __restrict__ tile_count,
@@ -190,7 +201,9 @@ __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
   const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)blockIdx.y * tiles_x + blockIdx.x;
   const int tid = threadIdx.x;
   const Cell* fcells = cells + (size_t)f * ncell;
-  const int nraw = __ldg(tile_count + tile);
+  const int craw = __ldg(tile_count + tile);
+  if (kBoundsOnly && !(craw & kEdgeFlag)) return;
+  const int nraw = craw & kCountMask;
   const bool overflow = nraw > kTileCap;
   const uint16_t* list = overflow ? nullptr : tile_list + tile * kTileCap;   // sorted by descending id
   const int ncand = overflow ? ncell : nraw;
@@ -264,6 +277,8 @@ __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
         }
       }
     }
+  }
+  if (active && !kBoundsOnly) {
     // 1/32-px source coordinates and the fixed-point blend (mfs.py:1063-1069)
     const uint32_t border = (uint32_t)bb | ((uint32_t)bg << 8) | ((uint32_t)br << 16);
     uint32_t o[kPix];
@@ -437,6 +452,44 @@ extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {
   return mf::align_up(cv.used, 256);
 }
 
+// memset + cell_setup + tile_sort: everything the pixel pass and the bounds-only pass share
+static int prepare_cells(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H, int R,
+                         int C, int32_t* crop_out, const mf::WarpWorkspace& w, cudaStream_t st) {
+  const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
+  cudaError_t ce = cudaMemsetAsync(w.tile_count, 0, (size_t)nf * tiles_x * tiles_y * sizeof(int), st);
+  if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "warp: memset: %s", cudaGetErrorString(ce));
+  const int64_t ncells = (int64_t)nf * R * C;
+  mf::cell_setup_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(
+      u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, w.tile_count, w.tile_list, crop_out);
+  if (int e = mf::check_launch("cell_setup")) return e;
+  const int64_t ntiles = (int64_t)nf * tiles_x * tiles_y;
+  mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
+  return mf::check_launch("tile_sort");
+}
+
+extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W,
+                                   int H, int R, int C, int32_t* crop_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  MF_REQUIRE(u && s && vertex_xy && crop_out && workspace, "mf_warp_crop_bounds: null pointer");
+  MF_REQUIRE(nf > 0 && nf <= 65535 && W > 1 && H > 1 && R > 0 && C > 0 && R * C <= 65535,
+             "mf_warp_crop_bounds: bad sizes");
+  mf::Carver cv(workspace, workspace_bytes);
+  mf::WarpWorkspace w;
+  if (!mf::carve_warp(cv, nf, W, H, R, C, w))
+    return mf::fail(MF_E_WORKSPACE, "mf_warp_crop_bounds: workspace %zu < %zu bytes", workspace_bytes, cv.used);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, st)) return e;
+  const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
+  const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
+  if ((W % mf::kTileW == 0) && (H % mf::kTileH == 0))
+    mf::warp_kernel<false, true, true><<<grid, mf::kWarpThreads, 0, st>>>(
+        nullptr, nullptr, w.cells, w.tile_count, w.tile_list, crop_out, nullptr, W, H, R * C, tiles_x, tiles_y, 0, 0, 0);
+  else
+    mf::warp_kernel<false, false, true><<<grid, mf::kWarpThreads, 0, st>>>(
+        nullptr, nullptr, w.cells, w.tile_count, w.tile_list, crop_out, nullptr, W, H, R * C, tiles_x, tiles_y, 0, 0, 0);
+  return mf::check_launch("warp_bounds");
+}
+
 extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s,
                               const float* vertex_xy, int nf, int W, int H, int R, int C, int border_b,
                               int border_g, int border_r, uint8_t* frames_out, int32_t* crop_out,
@@ -453,21 +506,13 @@ extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const d
     return mf::fail(MF_E_WORKSPACE, "mf_warp_frames: workspace %zu < %zu bytes", workspace_bytes, cv.used);
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
-  cudaError_t ce = cudaMemsetAsync(w.tile_count, 0, (size_t)nf * tiles_x * tiles_y * sizeof(int), st);
-  if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "mf_warp_frames: memset: %s", cudaGetErrorString(ce));
-  const int64_t ncells = (int64_t)nf * R * C;
-  mf::cell_setup_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(
-      u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, w.tile_count, w.tile_list, crop_out);
-  if (int e = mf::check_launch("cell_setup")) return e;
-  const int64_t ntiles = (int64_t)nf * tiles_x * tiles_y;
-  mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
-  if (int e = mf::check_launch("tile_sort")) return e;
+  if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, st)) return e;
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
   const bool full = (W % mf::kTileW == 0) && (H % mf::kTileH == 0);
 #define MF_LAUNCH_WARP(MAPS, FULL)                                                                        \
-  mf::warp_kernel<MAPS, FULL><<<grid, mf::kWarpThreads, 0, st>>>(frames_in, frames_out, w.cells, w.tile_count, \
-                                                                w.tile_list, crop_out, map_out, W, H, R * C,  \
-                                                                tiles_x, tiles_y, border_b, border_g, border_r)
+  mf::warp_kernel<MAPS, FULL, false><<<grid, mf::kWarpThreads, 0, st>>>(                                 \
+      frames_in, frames_out, w.cells, w.tile_count, w.tile_list, crop_out, map_out, W, H, R * C, tiles_x, \
+      tiles_y, border_b, border_g, border_r)
   if (map_out) { if (full) MF_LAUNCH_WARP(true, true); else MF_LAUNCH_WARP(true, false); }
   else { if (full) MF_LAUNCH_WARP(false, true); else MF_LAUNCH_WARP(false, false); }
 #undef MF_LAUNCH_WARP

@@ -79,3 +79,38 @@ def reduce_crop(crop_enc: torch.Tensor):
     if world > 1:
         dist.all_reduce(crop_enc, op=dist.ReduceOp.MAX)
     return crop_enc
+
+
+def sharded_paths(core, tracks_dev, frames_local, definition, pair_start_host=None):
+    """Unstabilized and stabilized vertex paths of the WHOLE video on every rank.
+
+    Each rank holds the tracks of its own ``frames_local`` frame pairs (pair t joins frames t and
+    t+1; the last rank's last pair is dropped because the video ends there).  Velocities and pair
+    homographies are all-gathered, the float64 prefix sum is replicated, the Jacobi solve is sharded
+    by vertex and the solved paths all-gathered.  Returns (u, s, homographies) with
+    ``world * frames_local`` frames each.
+    """
+    rank, world = world_info()
+    dev = core.device
+    tr = tracks_dev
+    vel = core.vertex_velocities(tr["early"], tr["late"], tr["offset"], tr["keep"], tr["pair_start"],
+                                 tr["homographies"], pair_start_host=pair_start_host)
+    total = world * frames_local
+    ident = torch.eye(3, dtype=torch.float64, device=dev).reshape(1, 9)
+    if world > 1:
+        counts = [int(vel.shape[0])] * world
+        vel_all = gather_velocities(vel, counts)[:total - 1]
+        homs = torch.cat([gather_velocities(tr["homographies"], counts)[:total - 1], ident])
+    else:
+        vel_all = vel[:total - 1]
+        homs = torch.cat([tr["homographies"][:total - 1], ident])
+    u = core.prefix_displacements(vel_all)
+    V = core.mesh.vertices
+    if world > 1:
+        v0, v1, _ = vertex_shard(V, world, rank)
+        s = torch.empty_like(u)
+        core.stabilized_displacements(u, homs, definition, vertex_range=(v0, v1), out=s)
+        s = gather_paths(s.view(total, V, 2), V).view(u.shape)
+    else:
+        s = core.stabilized_displacements(u, homs, definition)
+    return u, s, homs

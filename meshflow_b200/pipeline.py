@@ -144,6 +144,17 @@ class DeviceCore:
             b, g, r, _ptr(dst), _ptr(crop), _ptr(maps), _ptr(ws), ws.numel(), _stream()))
         return (dst, crop, maps) if return_maps else (dst, crop)
 
+    def warp_crop_bounds(self, u, s):
+        """Per-frame crop edges (nf,4) int32 exactly as ``warp_frames`` returns them, computed from the
+        vertex paths alone (no pixel is read): pass A of the streamed schedule."""
+        m = self.mesh
+        nf = int(u.shape[0])
+        crop = torch.empty((nf, 4), dtype=torch.int32, device=self.device)
+        ws = self._workspace("warp", self.lib.mf_warp_workspace_bytes(nf, m.width, m.height, m.rows, m.cols))
+        _cabi.check(self.lib.mf_warp_crop_bounds(_ptr(u), _ptr(s), _ptr(self.vertex_xy), nf, m.width, m.height,
+                                                 m.rows, m.cols, _ptr(crop), _ptr(ws), ws.numel(), _stream()))
+        return crop
+
     def combine_crop(self, per_frame_crop):
         """(nf,4) per-frame edges -> device int32[4] = [max left, max top, -min right, -min bottom]
         (mfs.py:1103-1106): encoded so that ONE max-reduction -- and one all_reduce(MAX) across GPUs --
@@ -188,3 +199,82 @@ class DeviceCore:
         _cabi.check(self.lib.mf_stability_ratios(_ptr(s), F, n_sys, _ptr(ratio), _stream()))
         r = ratio.view(-1, 2)
         return (r[:, 0].mean() + r[:, 1].mean()) / 2.0
+
+
+class StreamedCore:
+    """Host buffers in, host buffers out, with the copies hidden behind the kernels.
+
+    Schedule for one video (F frames in pinned host memory):
+
+    1. tracks H2D -> vertex motion -> prefix sum -> Jacobi            (needs no pixels, ~1 ms)
+    2. ``warp_crop_bounds`` over all frames -> crop rectangle          (needs no pixels either)
+    3. per chunk of frames, on three streams: H2D chunk | warp + crop/resize chunk | D2H chunk
+
+    so the PCIe link runs in both directions at once and the stabilized (uncropped) frames never
+    exist beyond one chunk.  Results are identical to the unstreamed stage sequence.
+    """
+
+    def __init__(self, core: DeviceCore, chunk_frames=16):
+        self.core = core
+        self.chunk = int(chunk_frames)
+        dev = core.device
+        self.copy_in = torch.cuda.Stream(device=dev)
+        self.copy_out = torch.cuda.Stream(device=dev)
+        self._bufs = None
+
+    def _buffers(self, n_slots, shape):
+        key = (n_slots, tuple(shape))
+        if self._bufs is None or self._bufs[0] != key:
+            dev = self.core.device
+            mk = lambda: [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
+            self._bufs = (key, mk(), mk(), torch.empty(shape, dtype=torch.uint8, device=dev))
+        return self._bufs[1], self._bufs[2], self._bufs[3]
+
+    def run(self, h_frames, tracks, h_out, definition):
+        """h_frames / h_out: pinned (F,H,W,3) uint8 CPU tensors holding THIS RANK's frames.  tracks:
+        dict of pinned CPU tensors (early, late, offset, keep, pair_start, homographies[P,9]) of this
+        rank's frame pairs (at least F-1 of them; F when another rank's frames follow).
+        Returns (crop_enc device tensor, u, s of the whole video) -- all work is enqueued, nothing is
+        synchronised."""
+        from . import distributed as mfd
+        core = self.core
+        dev = core.device
+        F = int(h_frames.shape[0])
+        main = torch.cuda.current_stream(dev)
+        rank, _ = mfd.world_info()
+        # 1. paths of the whole video (all-gathers / vertex-sharded solve when there are several ranks)
+        tr = {k: v.to(dev, non_blocking=True) for k, v in tracks.items()}
+        u_all, s_all, _ = mfd.sharded_paths(core, tr, F, definition, pair_start_host=tracks["pair_start"])
+        u, s = u_all[rank * F:(rank + 1) * F], s_all[rank * F:(rank + 1) * F]
+        # 2. crop rectangle of the whole video: local bounds, then one MAX all-reduce
+        enc = mfd.reduce_crop(core.combine_crop(core.warp_crop_bounds(u, s)))
+        # 3. chunked, triple-buffered pixel pass
+        n_slots = 3
+        cshape = (self.chunk,) + tuple(h_frames.shape[1:])
+        ins, outs, stab = self._buffers(n_slots, cshape)
+        in_ready = [torch.cuda.Event() for _ in range(n_slots)]
+        in_free = [None] * n_slots
+        out_ready = [torch.cuda.Event() for _ in range(n_slots)]
+        out_free = [None] * n_slots
+        starts = list(range(0, F, self.chunk))
+        for ci, f0 in enumerate(starts):
+            n = min(self.chunk, F - f0)
+            slot = ci % n_slots
+            with torch.cuda.stream(self.copy_in):
+                if in_free[slot] is not None:
+                    self.copy_in.wait_event(in_free[slot])      # the warp that last read this slot is done
+                ins[slot][:n].copy_(h_frames[f0:f0 + n], non_blocking=True)
+                in_ready[slot].record(self.copy_in)
+            main.wait_event(in_ready[slot])
+            if out_free[slot] is not None:
+                main.wait_event(out_free[slot])                 # the D2H that last read this slot is done
+            core.warp_frames(ins[slot][:n], u[f0:f0 + n], s[f0:f0 + n], out=stab[:n])
+            e = torch.cuda.Event(); e.record(main); in_free[slot] = e
+            core.crop_resize_device(stab[:n], enc, out=outs[slot][:n])
+            out_ready[slot].record(main)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(out_ready[slot])
+                h_out[f0:f0 + n].copy_(outs[slot][:n], non_blocking=True)
+                e2 = torch.cuda.Event(); e2.record(self.copy_out); out_free[slot] = e2
+        main.wait_stream(self.copy_out)
+        return enc, u_all, s_all

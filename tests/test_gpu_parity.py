@@ -161,6 +161,8 @@ def test_warp_matches_oracle(W, H, R, C, F, amp):
         assert crop[f].tolist() == ref_pf[f].tolist()
     enc = core.combine_crop(torch.from_numpy(crop).to(core.device))
     assert core.decode_crop(enc) == tuple(ref_crop)
+    bounds = core.warp_crop_bounds(_dev(u, core), _dev(s, core)).cpu().numpy()       # pass A: no pixels read
+    assert np.array_equal(bounds, crop)
     if ref_crop[0] <= ref_crop[2] and ref_crop[1] <= ref_crop[3]:
         a = core.crop_resize_device(torch.from_numpy(out).to(core.device), enc).cpu().numpy()
         b = core.crop_resize(torch.from_numpy(out).to(core.device), ref_crop).cpu().numpy()
@@ -197,3 +199,33 @@ def test_stability_score_matches_oracle():
     got = float(core.stability_score(_dev(u, core)).item())
     from oracle import reference_port as port
     assert abs(got - port.stability_score(u)) <= 1e-10 * abs(got)
+
+
+def test_streamed_schedule_equals_stage_sequence():
+    """Host buffers in / out with chunked, overlapped copies must give the very same bytes."""
+    from meshflow_b200 import StreamedCore
+    W, H, R, C, F = 320, 180, 8, 8, 23
+    rng = np.random.default_rng(77)
+    frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+    tr = synth.synthetic_tracks(rng, F - 1, 500, W, H)
+    core = _core(W, H, R, C)
+    vel = core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
+                                 _dev(tr["keep"], core), _dev(tr["pair_start"], core),
+                                 _dev(tr["homographies"].reshape(-1, 9), core), pair_start_host=tr["pair_start"])
+    u = core.prefix_displacements(vel)
+    homs = torch.cat([_dev(tr["homographies"].reshape(-1, 9), core), torch.eye(3, dtype=torch.float64, device=core.device).reshape(1, 9)])
+    s = core.stabilized_displacements(u, homs, 2)
+    stab, crop_pf = core.warp_frames(_dev(frames, core), u, s)
+    enc = core.combine_crop(crop_pf)
+    ref = core.crop_resize_device(stab, enc).cpu().numpy()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    tracks = {k: pin(tr[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
+    tracks["homographies"] = pin(tr["homographies"].reshape(-1, 9))
+    h_out = torch.zeros((F, H, W, 3), dtype=torch.uint8).pin_memory()
+    sc = StreamedCore(core, chunk_frames=5)
+    for _ in range(2):                                        # second run reuses every buffer
+        enc2, u2, s2 = sc.run(pin(frames), tracks, h_out, 2)
+        torch.cuda.synchronize()
+        assert core.decode_crop(enc2) == core.decode_crop(enc)
+        assert torch.equal(u2, u) and torch.equal(s2, s)
+        assert np.array_equal(h_out.numpy(), ref)
