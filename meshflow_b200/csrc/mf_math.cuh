@@ -453,6 +453,18 @@ MF_HD void remap_coords(float mx, float my, int& ix, int& iy, int& ax, int& ay) 
   ix = sx >> 5; iy = sy >> 5; ax = sx & 31; ay = sy & 31;
 }
 
+// remap_coords for map values that are known not to be NaN (every value a cell produces is finite:
+// a cell with a non-finite homography is never "inside"); saves the NaN select of round_sat_f.
+MF_HD void remap_coords_finite(float mx, float my, int& ix, int& iy, int& ax, int& ay) {
+#if defined(__CUDA_ARCH__)
+  const int sx = __float2int_rn(MF_FMUL(mx, 32.0f));
+  const int sy = __float2int_rn(MF_FMUL(my, 32.0f));
+  ix = sx >> 5; iy = sy >> 5; ax = sx & 31; ay = sy & 31;
+#else
+  remap_coords(mx, my, ix, iy, ax, ay);
+#endif
+}
+
 MF_HD int blend4(int p00, int p01, int p10, int p11, int ax, int ay) {
   return (p00 * (32 - ax) * (32 - ay) + p01 * ax * (32 - ay) + p10 * (32 - ax) * ay + p11 * ax * ay + 512) >> 10;
 }

@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(128) tile_sort_kernel(const int* __restrict__ 
 // Per-pixel (general) resolution of one output pixel against a list of candidate cells (descending
 // id; list == nullptr: every cell of the frame).  Rare path: group straddles a cell edge, cell not
 // screenable, frame border.
-__device__ __forceinline__ void resolve_pixel(const Cell* __restrict__ fcells, const uint16_t* __restrict__ list,
-                                              int n, int px, int py, float& mx, float& my) {
+__device__ __forceinline__ float2 resolve_pixel(const Cell* __restrict__ fcells, const uint16_t* __restrict__ list,
+                                             int n, int px, int py, float mx, float my) {
   const double x = (double)px, y = (double)py;
   for (int k = 0; k < n; ++k) {
     const Cell& c = fcells[list ? (int)__ldg(list + k) : n - 1 - k];
@@ -120,8 +120,9 @@ __device__ __forceinline__ void resolve_pixel(const Cell* __restrict__ fcells, c
                        fmaf(c.fm[7], fy, c.fm[8]));
     }
     if (in < 0) in = cell_inside(c, x, y) ? 1 : 0;
-    if (in == 1) { cell_map(c, x, y, mx, my); return; }
+    if (in == 1) { cell_map(c, x, y, mx, my); break; }
   }
+  return make_float2(mx, my);
 }
 
 // Four taps of one output pixel, all inside the frame, regrouped per channel.  Each source row
@@ -244,7 +245,10 @@ __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
     if (general) {
 #pragma unroll
       for (int j = 0; j < kPix; ++j)
-        if (j < npx) resolve_pixel(fcells, list, ncand, px0 + j, py, mx[j], my[j]);
+        if (j < npx) {
+          const float2 m = resolve_pixel(fcells, list, ncand, px0 + j, py, mx[j], my[j]);
+          mx[j] = m.x; my[j] = m.y;
+        }
     } else if (hit != nullptr) {
       const double2* hs = reinterpret_cast<const double2*>(hit->Hsu);
       const double2 h01 = __ldg(hs), h23 = __ldg(hs + 1), h45 = __ldg(hs + 2), h67 = __ldg(hs + 3);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
       int ix, iy, ax, ay;
-      remap_coords(mx[j], my[j], ix, iy, ax, ay);
+      remap_coords_finite(mx[j], my[j], ix, iy, ax, ay);
       if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
         o[j] = blend_interior(src, W * 3, ix, iy, ax, ay);
       } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {

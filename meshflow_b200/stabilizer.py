@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import host_features
-from .pipeline import DeviceCore, MeshSpec
+from .pipeline import DeviceCore, MeshSpec, StreamedCore
 
 
 class MeshFlowStabilizer:
@@ -43,7 +43,7 @@ class MeshFlowStabilizer:
                  homography_min_number_corresponding_features=4,
                  temporal_smoothing_radius=10, optimization_num_iterations=100,
                  color_outside_image_area_bgr=(0, 0, 255),
-                 visualize=False, *, device=None, host_workers=None):
+                 visualize=False, *, device=None, host_workers=None, chunk_frames=16):
         self.mesh_col_count = mesh_col_count
         self.mesh_row_count = mesh_row_count
         self.mesh_outlier_subframe_row_count = mesh_outlier_subframe_row_count
@@ -59,6 +59,7 @@ class MeshFlowStabilizer:
         # extensions (keyword only, not in the reference)
         self.device = device
         self.host_workers = host_workers
+        self.chunk_frames = chunk_frames
         self._cores = {}
 
     # ------------------------------------------------------------------------------------------
@@ -81,26 +82,37 @@ class MeshFlowStabilizer:
         ``homographies``, ``s`` (NumPy) and the three metrics."""
         self._validate_definition(adaptive_weights_definition)
         num_frames = len(unstabilized_frames)
+        if num_frames < 2:
+            raise ValueError("need at least two frames to stabilize")
         height, width = unstabilized_frames[0].shape[:2]
         core = self._core(width, height)
         tracks = self._track(unstabilized_frames[:-1], unstabilized_frames[1:])
-        frames_d = self._upload_frames(core, unstabilized_frames)
-        u_d, homs = self._device_displacements(core, tracks)
-        homs_d = torch.from_numpy(homs).to(core.device)
-        s_d = core.stabilized_displacements(u_d, homs_d, adaptive_weights_definition)
-        stab_d, crop_pf = core.warp_frames(frames_d, u_d, s_d)
-        crop_enc = core.combine_crop(crop_pf)
-        cropped_d = core.crop_resize_device(stab_d, crop_enc)
-        crop = self._crop_tuple(crop_enc)
-        self._check_crop(crop, width, height)
+        packed = self.pack_tracks(tracks)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_tracks = {k: pin(packed[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
+        h_tracks["homographies"] = pin(packed["homographies"].reshape(-1, 9))
+        h_frames = torch.empty((num_frames, height, width, 3), dtype=torch.uint8, pin_memory=True)
+        view = h_frames.numpy()
+        for i, f in enumerate(unstabilized_frames):
+            view[i] = f
+        h_out = torch.empty_like(h_frames, pin_memory=True)
+        # host buffers in, host buffers out: copies overlap the kernels (pipeline.StreamedCore)
+        crop_enc, u_d, s_d = StreamedCore(core, self.chunk_frames).run(h_frames, h_tracks, h_out,
+                                                                       adaptive_weights_definition)
         stability = core.stability_score(s_d) if with_metrics else None
-        cropped = cropped_d.cpu().numpy()
+        crop = self._crop_tuple(crop_enc)                    # synchronises
+        torch.cuda.synchronize(core.device)
+        self._check_crop(crop, width, height)
+        cropped = h_out.numpy()
         cropped_frames = [cropped[i] for i in range(num_frames)]
+        homs = np.empty((num_frames, 3, 3))
+        homs[:-1] = packed["homographies"]
+        homs[-1] = np.identity(3)                            # mfs.py:273-274
         out = dict(cropped_frames=cropped_frames, crop_boundaries=crop, u=u_d.cpu().numpy(), homographies=homs,
                    s=s_d.cpu().numpy())
         if with_metrics:
             cr, ds = self._compute_cropping_ratio_and_distortion_score(num_frames, unstabilized_frames, cropped_frames)
-            out.update(cropping_ratio=cr, distortion_score=ds, stability_score=float(stability.item()))
+            out.update(cropping_ratio=cr, distortion_score=ds, stability_score=np.float64(stability.item()))
         return out
 
     # ------------------------------------------------------------------------------------------

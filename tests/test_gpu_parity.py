@@ -229,3 +229,66 @@ def test_streamed_schedule_equals_stage_sequence():
         assert core.decode_crop(enc2) == core.decode_crop(enc)
         assert torch.equal(u2, u) and torch.equal(s2, s)
         assert np.array_equal(h_out.numpy(), ref)
+
+
+def test_stabilize_frames_matches_the_reference_port_end_to_end():
+    """Whole pipeline on a small synthetic video through the drop-in class (host OpenCV front end,
+    streamed GPU core, host metrics) against the CPU port of the reference."""
+    from meshflow_b200 import MeshFlowStabilizer
+    from oracle import reference_port as port
+    frames = synth.textured_video(np.random.default_rng(12), 14, 320, 180, jitter=2.0)
+    for definition in (0, 2):
+        ref = port.stabilize_frames(port.Params(mesh_row_count=8, mesh_col_count=8), frames, definition)
+        got = MeshFlowStabilizer(mesh_row_count=8, mesh_col_count=8, chunk_frames=4).stabilize_frames(frames, definition)
+        assert np.array_equal(got["u"], ref["u"]) and np.array_equal(got["homographies"], ref["homographies"])
+        assert np.abs(got["s"] - ref["s"]).max() <= 1e-9 * max(1.0, np.abs(ref["s"]).max())
+        assert tuple(int(c) for c in got["crop_boundaries"]) == tuple(int(c) for c in ref["crop"])
+        assert all(np.array_equal(a, b) for a, b in zip(got["cropped_frames"], ref["cropped"]))
+        # the three returned metrics: within 1e-4 relative (north star); types as the reference's
+        assert abs(got["cropping_ratio"] - ref["cropping_ratio"]) <= 1e-4 * abs(ref["cropping_ratio"])
+        assert abs(got["distortion_score"] - ref["distortion_score"]) <= 1e-4 * abs(ref["distortion_score"])
+        assert abs(got["stability_score"] - ref["stability_score"]) <= 1e-4 * abs(ref["stability_score"])
+        assert isinstance(got["cropping_ratio"], np.float32) and isinstance(got["stability_score"], np.float64)
+
+
+def test_reference_named_stage_methods_against_goldens():
+    """The reference's private stage methods, same names and signatures, fed with the committed golden
+    inputs produced by the unmodified reference (tests/golden/make_golden.py)."""
+    import os
+    from meshflow_b200 import MeshFlowStabilizer
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(G, "video1_motion_paths.npz"))
+    w, h = (int(v) for v in g["frame_size"])
+    st = MeshFlowStabilizer()
+    dummy = [np.zeros((h, w, 3), np.uint8)]
+    for d in range(4):
+        s = st._get_stabilized_vertex_displacements(13, dummy, d, g["u"], g["homographies"])
+        assert np.abs(s - g[f"s_{d}"]).max() <= 1e-9 * np.abs(g[f"s_{d}"]).max()
+        lam = st._get_adaptive_weights(13, w, h, d, g["homographies"])
+        assert np.allclose(lam, g[f"lambda_{d}"], rtol=1e-12, atol=0)
+        assert abs(st._compute_stability_score(13, g[f"s_{d}"]) - float(g[f"stability_{d}"])) <= 1e-10
+    gw = np.load(os.path.join(G, "warp_small.npz"))
+    frames = list(gw["frames"])
+    st8 = MeshFlowStabilizer(mesh_row_count=8, mesh_col_count=8, color_outside_image_area_bgr=(10, 200, 30))
+    for case in ("mild", "wild"):
+        stab, crop = st8._get_stabilized_frames_and_crop_boundaries(3, frames, gw[f"{case}_u"], gw[f"{case}_s"])
+        assert np.array_equal(np.stack(stab), gw[f"{case}_stabilized"])
+        assert [int(c) for c in crop] == gw[f"{case}_crop"].tolist() and isinstance(crop[0], np.int64)
+        if f"{case}_cropped" in gw:
+            assert np.array_equal(np.stack(st8._crop_frames(stab, crop)), gw[f"{case}_cropped"])
+    # vertex motion from the golden matched features (device masks = all kept)
+    from meshflow_b200 import DeviceCore, MeshSpec
+    core = DeviceCore(MeshSpec(w, h, 16, 16))
+    for t in range(4):
+        e, l = g[f"early_{t}"], g[f"late_{t}"]
+        n = len(e)
+        # the reference's features are float32 subframe coordinates + the integer subframe origin (same
+        # origin for the early and the late point); the golden holds the float64 sums
+        off = np.stack([np.floor(e[:, 0] / 160.0) * 160, np.floor(e[:, 1] / 90.0) * 90], axis=1)
+        es, ls = (e - off).astype(np.float32), (l - off).astype(np.float32)
+        assert np.array_equal(es.astype(np.float64) + off, e) and np.array_equal(ls.astype(np.float64) + off, l)
+        vel = core.vertex_velocities(_dev(es, core), _dev(ls, core), _dev(off.astype(np.int32), core),
+                                     _dev(np.ones(n, np.uint8), core), _dev(np.array([0, n], np.int32), core),
+                                     _dev(g["pair_homographies"][t].reshape(1, 9), core),
+                                     pair_start_host=np.array([0, n], np.int32)).cpu().numpy()[0]
+        assert np.array_equal(vel, g["velocities"][t])
