@@ -221,7 +221,15 @@ __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
 #pragma unroll
   for (int j = 0; j < kPix; ++j) { mx[j] = (float)(W + 1); my[j] = (float)(H + 1); }   // mfs.py:983-984
 
+#if defined(MF_EXPERIMENT_NO_MAP)      // timing experiment only: cost of everything except cell search + map
   if (active) {
+#pragma unroll
+    for (int j = 0; j < kPix; ++j) { mx[j] = (float)(px0 + j) + 3.3f; my[j] = (float)py + 2.2f; }
+  }
+  if (false) {
+#else
+  if (active) {
+#endif
     // group decision: the first candidate (descending id) that certainly contains both end pixels
     // contains the whole group; candidates both end pixels are certainly beyond on one side are skipped
     const Cell* hit = nullptr;
@@ -290,6 +298,9 @@ __global__ void __launch_bounds__(kWarpThreads, MF_WARP_MINBLOCKS) warp_kernel(
     for (int j = 0; j < kPix; ++j) {
       int ix, iy, ax, ay;
       remap_coords_finite(mx[j], my[j], ix, iy, ax, ay);
+#if defined(MF_EXPERIMENT_NO_GATHER)   // timing experiment only: cost of everything except the tap gathers
+      if (true) { o[j] = (uint32_t)(ix * 7 + iy * 3 + ax + ay) & 0x00ffffffu; } else
+#endif
       if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
         o[j] = blend_interior(src, W * 3, ix, iy, ax, ay);
       } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {

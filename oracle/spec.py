@@ -314,10 +314,12 @@ def warp_maps(W, H, cells, prune=True):
         mild = False
         if prune:
             # the quad's bounding box only bounds the support while the cell's projective
-            # denominator stays near 1 on the rest rectangle (no fold, no horizon crossing)
+            # denominator keeps its sign and hardly varies over the rest rectangle (no fold, no
+            # horizon crossing)
             hus = cells["Hus"][n]
             wq = cells["src"][n][:, 0] * hus[6] + cells["src"][n][:, 1] * hus[7] + hus[8]
-            mild = bool(np.all(np.isfinite(wq)) and wq.min() > 0.5 and wq.max() < 2.0)
+            aw = np.abs(wq)
+            mild = bool(np.all(np.isfinite(wq)) and (np.all(wq > 0) or np.all(wq < 0)) and aw.max() < 1.5 * aw.min())
         if mild:
             q = cells["dst"][n]
             x0 = max(0, int(math.floor(q[:, 0].min())) - 3); x1 = min(W - 1, int(math.ceil(q[:, 0].max())) + 3)
