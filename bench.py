@@ -340,7 +340,10 @@ def run_b200(args):
         "stages_ms": stage_ms,
         "roofline": {"kernel": "warp_kernel (mf_warp_frames, incl. cell_setup)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     # dram__bytes_read+write of this kernel from profiles/r01b_summary.md (ncu --set full,
+                     # 60 frames of 1080p: 387.6 MB + 338.3 MB), scaled to this launch's frame count
+                     "traffic": (387.63e6 + 338.31e6) / 60.0 * F * (W * H) / (1920.0 * 1080.0),
+                     "traffic_source": "profiles/r01b_summary.md", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": warp_bytes},
         "crop_resize_gbs": resize_gbs,
         "clocks": clocks,
