@@ -7,10 +7,13 @@ NVCC="${NVCC:-nvcc}"
 FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a
        -Xcompiler -fPIC,-O2,-ffp-contract=off --expt-relaxed-constexpr ${MF_NVCC_EXTRA:-})
 objs=()
+pids=()
 for f in cabi vertex_motion jacobi warp stability; do
+  rm -f "${here}/${f}.o"
   "${NVCC}" "${FLAGS[@]}" -c "${here}/${f}.cu" -o "${here}/${f}.o" &
+  pids+=($!)
   objs+=("${here}/${f}.o")
 done
-wait
+for p in "${pids[@]}"; do wait "$p" || { echo "nvcc failed" >&2; exit 1; }; done
 "${NVCC}" -shared -gencode arch=compute_100a,code=sm_100a -o "${out}" "${objs[@]}"
 echo "built ${out}"

@@ -421,11 +421,28 @@ MF_HD void cell_map(const Cell& c, double x, double y, float& mx, float& my) {
 // cell_map with the row products y*Hsu[1], y*Hsu[4], y*Hsu[7] supplied by the caller: every rounding
 // is the one cell_map performs, so the result is bit-identical; 1/w is the correctly rounded
 // reciprocal either way.
+// Correctly rounded 1/w for a finite, normal w well inside the exponent range (the remap denominator
+// is ~1): hardware seed (2^-23), two Newton steps (-> within an ulp), then Markstein's final
+// correction y + y*(1 - w*y), which rounds correctly (the only exception, an all-ones significand,
+// has probability 2^-52 and would cost one ulp).  Same value as __drcp_rn / IEEE 1.0/w without the
+// special-case handling; checked against __drcp_rn on the device by mf_debug_rcp_mismatches.
+#if defined(__CUDACC__)
+__device__ __forceinline__ double rcp_rn_normal(double w) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+  double e = fma(-w, y, 1.0); y = fma(y, e, y);
+  e = fma(-w, y, 1.0); y = fma(y, e, y);
+  e = fma(-w, y, 1.0); y = fma(y, e, y);
+  return y;
+}
+#endif
+
 MF_HD void map_row(double h0, double h2, double h3, double h5, double h6, double x, double yh1, double yh4,
                    double yh7, float& mx, float& my) {
   double w = MF_ADD(MF_ADD(MF_MUL(x, h6), yh7), 1.0);
 #if defined(__CUDA_ARCH__)
-  w = (fabs(w) > 2.220446049250313e-16) ? __drcp_rn(w) : 0.0;
+  const double aw = fabs(w);
+  w = (aw > 1e-100 && aw < 1e100) ? rcp_rn_normal(w) : ((aw > 2.220446049250313e-16) ? __drcp_rn(w) : 0.0);
 #else
   w = (fabs(w) > 2.220446049250313e-16) ? (1.0 / w) : 0.0;
 #endif

@@ -292,3 +292,16 @@ def test_reference_named_stage_methods_against_goldens():
                                      _dev(g["pair_homographies"][t].reshape(1, 9), core),
                                      pair_start_host=np.array([0, n], np.int32)).cpu().numpy()[0]
         assert np.array_equal(vel, g["velocities"][t])
+
+
+def test_fast_reciprocal_is_correctly_rounded():
+    """The warp kernel's reciprocal (hardware seed + Newton + Markstein correction) must equal the
+    IEEE correctly rounded 1/w bit for bit: 200 M random doubles, 1/8 of them in the w ~ 1 regime."""
+    import ctypes
+    from meshflow_b200 import _cabi
+    lib = _cabi.load()
+    lib.mf_debug_rcp_mismatches.restype = ctypes.c_longlong
+    lib.mf_debug_rcp_mismatches.argtypes = [ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+    scratch = torch.zeros(1, dtype=torch.int64, device="cuda")
+    bad = lib.mf_debug_rcp_mismatches(200_000_000, 12345, scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert bad == 0
