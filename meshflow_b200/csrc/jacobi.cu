@@ -13,6 +13,7 @@
 //                         every sweep without leaving the SM: HBM is touched twice (load b, store x).
 #include "mf_common.cuh"
 #include "mf_math.cuh"
+#include <cmath>
 
 namespace mf {
 
@@ -187,6 +188,72 @@ __global__ void __launch_bounds__(512) jacobi_solve_long_kernel(
   for (int t = tid; t < F; t += nt) *reinterpret_cast<double2*>(s + (size_t)t * n_sys + q) = xs[t];
 }
 
+// Register-window variant for long videos (F up to T*512 frames).  One CTA per SYSTEM (vertex
+// component).  Thread t owns the T consecutive frames [T t, T t + T): per sweep it streams the
+// T + 2 RADIUS inputs it needs through registers once and accumulates every (input, output) pair with
+// compile-time offsets -- T (2 RADIUS + 1) FMAs for T + 2 RADIUS shared-memory reads, instead of one
+// read per FMA.  The trajectory lives in shared memory in a [T][threads] layout (frame T t + i at
+// [i][t]) so that every access of a warp is to consecutive words; the right-hand side is kept there
+// too as B = b / diag, the per-frame gain g = 2 lambda / diag in registers, the weights in the
+// kernel-parameter constant bank.  x' = B + g * sum_k w_k x_{t+k}  ==  (b + 2 lambda sum) / diag.
+struct JacobiWeights { double w[32]; };   // w[|k|], k <= 31
+
+template <int T, int RADIUS>
+__global__ void __launch_bounds__(512) jacobi_window_kernel(
+    const double* __restrict__ u, double* __restrict__ s, int F, int64_t n_sys, int64_t sys_begin, int iterations,
+    const double* __restrict__ inv_diag, const double* __restrict__ two_lambda, const JacobiWeights wts) {
+  constexpr int HP = (RADIUS + T - 1) / T;          // pad columns either side (frames of absent neighbours)
+  extern __shared__ double sm[];
+  const int nt = blockDim.x, t = threadIdx.x;
+  const int ntp = nt + 2 * HP;
+  double* xs = sm;                                   // [T][ntp]
+  double* bs = sm + T * ntp;                         // [T][nt]
+  const int64_t q = sys_begin + blockIdx.x;
+  for (int i = t; i < T * ntp; i += nt) xs[i] = 0.0;
+  __syncthreads();
+  double g[T];
+#pragma unroll
+  for (int i = 0; i < T; ++i) {
+    const int f = T * t + i;
+    double b = 0.0, id = 0.0, tl = 0.0;
+    if (f < F) { b = u[(size_t)f * n_sys + q]; id = inv_diag[f]; tl = two_lambda[f]; }
+    xs[i * ntp + t + HP] = b;
+    bs[i * nt + t] = id * b;
+    g[i] = id * tl;
+  }
+  __syncthreads();
+  for (int it = 0; it < iterations; ++it) {
+    double acc[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < T + 2 * RADIUS; ++j) {
+      constexpr int kBias = 64 * T;                  // keeps the division below on non-negative numbers
+      const int jj = j - RADIUS;                      // input frame relative to this thread's first frame
+      const int dt = (jj + kBias) / T - 64, ii = (jj + kBias) % T;
+      const double v = xs[ii * ntp + t + HP + dt];
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        const int d = jj - i;
+        if (d >= -RADIUS && d <= RADIUS) acc[i] = fma(wts.w[d < 0 ? -d : d], v, acc[i]);
+      }
+    }
+    double nx[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) nx[i] = fma(g[i], acc[i], bs[i * nt + t]);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+      if (T * t + i < F) xs[i * ntp + t + HP] = nx[i];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < T; ++i) {
+    const int f = T * t + i;
+    if (f < F) s[(size_t)f * n_sys + q] = xs[i * ntp + t + HP];
+  }
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) {
@@ -221,6 +288,28 @@ static int launch_solve(const double* u, double* s, int F, int64_t n_sys, int64_
     auto k = jacobi_solve_kernel<RADIUS, 4>;
     if (int e = set_smem(k, smem)) return e;
     k<<<grid, nt, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
+  } else if (radius == 30 || radius == 10) {
+    // long videos with the two radii the reference's users run: register-window kernel, CTA per system
+    constexpr int T = 20;
+    if (F > T * 512) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds %d frames per solve", F, T * 512);
+    const int nt = ((F + T - 1) / T + 31) / 32 * 32;
+    const int hp = (radius + T - 1) / T;
+    const size_t wsmem = ((size_t)T * (nt + 2 * hp) + (size_t)T * nt) * sizeof(double);
+    JacobiWeights wts;
+    for (int k = 0; k < 32; ++k) {
+      const double a = (3.0 / (double)radius) * (double)k;
+      wts.w[k] = k <= radius ? exp(-(a * a)) : 0.0;
+    }
+    const dim3 wgrid((unsigned)(2 * n_vert));
+    if (radius == 30) {
+      auto k = jacobi_window_kernel<T, 30>;
+      if (int e = set_smem(k, wsmem)) return e;
+      k<<<wgrid, nt, wsmem, st>>>(u, s, F, n_sys, sys_begin, iterations, inv_diag, two_lambda, wts);
+    } else {
+      auto k = jacobi_window_kernel<T, 10>;
+      if (int e = set_smem(k, wsmem)) return e;
+      k<<<wgrid, nt, wsmem, st>>>(u, s, F, n_sys, sys_begin, iterations, inv_diag, two_lambda, wts);
+    }
   } else {
     if (F > 20 * 512) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds 10240 frames per solve", F);
     auto k = jacobi_solve_long_kernel<0>;

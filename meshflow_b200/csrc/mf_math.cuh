@@ -158,27 +158,29 @@ MF_HD double adaptive_lambda(const double* Hm, int W, int H, int definition) {
   if (definition == 2) return 100.0;
   if (definition == 3) return 1.0;
   const double a = Hm[0], b = Hm[1], tx = Hm[2], c = Hm[3], d = Hm[4], ty = Hm[5];
-  const double tr = a + d;
-  const double det = a * d - b * c;
-  const double disc = tr * tr - 4.0 * det;
+  // explicit roundings (no FMA contraction): near a double eigenvalue the discriminant decides the
+  // branch, and the oracle's NumPy closed form rounds every product
+  const double tr = MF_ADD(a, d);
+  const double det = MF_SUB(MF_MUL(a, d), MF_MUL(b, c));
+  const double disc = MF_SUB(MF_MUL(tr, tr), MF_MUL(4.0, det));
   double m1, m2;
   if (disc >= 0.0) {
-    const double sq = sqrt(disc);
-    m1 = fabs((tr + sq) / 2.0);
-    m2 = fabs((tr - sq) / 2.0);
+    const double sq = MF_SQRT(disc);
+    m1 = fabs(MF_DIV(MF_ADD(tr, sq), 2.0));
+    m2 = fabs(MF_DIV(MF_SUB(tr, sq), 2.0));
   } else {
-    m1 = m2 = sqrt(fabs(det));
+    m1 = m2 = MF_SQRT(fabs(det));
   }
   // sort {1, m1, m2} ascending -> ratio = middle / largest
   double lo = 1.0, mid = m1, hi = m2, t;
   if (lo > mid) { t = lo; lo = mid; mid = t; }
   if (mid > hi) { t = mid; mid = hi; hi = t; }
   if (lo > mid) { t = lo; lo = mid; mid = t; }
-  const double ratio = mid / hi;
-  const double qx = tx / (double)W, qy = ty / (double)H;
-  const double trans = sqrt(qx * qx + qy * qy);
-  const double c1 = -1.93 * trans + 0.95;
-  const double c2 = (definition == 0) ? 5.83 * ratio + 4.88 : 5.83 * ratio - 4.88;
+  const double ratio = MF_DIV(mid, hi);
+  const double qx = MF_DIV(tx, (double)W), qy = MF_DIV(ty, (double)H);
+  const double trans = MF_SQRT(MF_ADD(MF_MUL(qx, qx), MF_MUL(qy, qy)));
+  const double c1 = MF_ADD(MF_MUL(-1.93, trans), 0.95);
+  const double c2 = (definition == 0) ? MF_ADD(MF_MUL(5.83, ratio), 4.88) : MF_SUB(MF_MUL(5.83, ratio), 4.88);
   const double m = c1 < c2 ? c1 : c2;
   return m > 0.0 ? m : 0.0;
 }

@@ -424,8 +424,9 @@ __global__ void __launch_bounds__(128) crop_resize_kernel(
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const int s0 = (int)__dp2a_lo(wx[j], q[ch], 0u), s1 = (int)__dp2a_hi(wx[j], q[ch], 0u);
+          // a0 + a1 <= 2049 and b0 + b1 <= 2049 bound the result by 255: no clamp needed
           const int v = (((yt.z * (s0 >> 4)) >> 16) + ((yt.w * (s1 >> 4)) >> 16) + 2) >> 2;
-          acc |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
+          acc |= (uint32_t)v << (8 * ch);
         }
       } else {
         const uint8_t* r0 = src + row0;

@@ -106,7 +106,8 @@ def test_prefix_sum_is_sequential_float64():
 # (2) Jacobi
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("F,R,radius,iters", [(12, 4, 10, 100), (300, 16, 10, 100), (700, 6, 10, 60),
-                                              (1500, 4, 7, 40), (2600, 2, 30, 25), (300, 4, 30, 50)])
+                                              (1500, 4, 7, 40), (2600, 2, 30, 25), (300, 4, 30, 50),
+                                              (3100, 2, 10, 30), (2300, 2, 12, 20)])
 @pytest.mark.parametrize("definition", [0, 1, 2, 3])
 def test_jacobi_matches_oracle(F, R, radius, iters, definition):
     rng = np.random.default_rng(F + definition)
@@ -115,7 +116,7 @@ def test_jacobi_matches_oracle(F, R, radius, iters, definition):
     s, lam = core.stabilized_displacements(_dev(u, core), _dev(homs, core), definition, return_lambda=True)
     s = s.cpu().numpy(); lam = lam.cpu().numpy()
     ref = spec.jacobi_banded(u, homs, 640, 360, radius, iters, definition)
-    assert np.allclose(lam, spec.adaptive_lambda(homs, 640, 360, definition), rtol=1e-12, atol=1e-14)
+    assert np.allclose(lam, spec.adaptive_lambda(homs, 640, 360, definition), rtol=1e-10, atol=1e-14)
     scale = np.abs(ref).max()
     assert np.abs(s - ref).max() <= 1e-9 * scale            # north-star tolerance: 1e-4 relative
 
