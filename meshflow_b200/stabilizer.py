@@ -18,7 +18,6 @@ fallback for the three stages.
 """
 from __future__ import annotations
 
-import math
 
 import cv2
 import numpy as np

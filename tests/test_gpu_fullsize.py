@@ -143,3 +143,25 @@ def test_two_frame_video_runs_through_every_stage():
     out, crop = core.warp_frames(_dev(frames, core), u, s)
     ref_frames, ref_crop = spec.warp_stage(list(frames), u.cpu().numpy(), s.cpu().numpy(), R, C, (0, 0, 255))
     assert np.array_equal(out.cpu().numpy(), np.stack(ref_frames))
+
+
+def test_config3_geometry_streamed_equals_stage_sequence():
+    """c3 geometry (4K, 32x32 mesh, CONSTANT_HIGH) on a short clip: host-in/host-out streamed schedule
+    == resident stage sequence, and the bounds-only pass == the pixel pass."""
+    from meshflow_b200 import StreamedCore
+    W, H, R, F = 3840, 2160, 32, 20
+    rng = np.random.default_rng(4321)
+    frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+    tr = synth.synthetic_tracks(rng, F - 1, 2500, W, H)
+    core = _core(W, H, R, R)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    tracks = {k: pin(tr[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
+    tracks["homographies"] = pin(tr["homographies"].reshape(-1, 9))
+    h_out = torch.zeros((F, H, W, 3), dtype=torch.uint8).pin_memory()
+    enc, u, s = StreamedCore(core, chunk_frames=8).run(pin(frames), tracks, h_out, 2)
+    torch.cuda.synchronize()
+    stab, crop_pf = core.warp_frames(_dev(frames, core), u, s)
+    assert torch.equal(core.combine_crop(crop_pf), enc)
+    assert torch.equal(core.warp_crop_bounds(u, s), crop_pf)
+    ref = core.crop_resize_device(stab, enc).cpu().numpy()
+    assert np.array_equal(h_out.numpy(), ref)
