@@ -257,7 +257,8 @@ struct alignas(16) Cell {
   double Hsu[8];                // stabilized -> unstabilized homography (h22 == 1), gives the remap coordinates
   double Mi[9];                 // inverse of the unstabilized -> stabilized homography, decides membership
   int lo_x, hi_x, lo_y, hi_y;   // membership bounds on the 1/32-px source coordinate (inclusive)
-  int pad2_[2];
+  int bounded;                  // 1: the support box is the bounded image of the grown rest rectangle; 0: "anywhere"
+  int pad2_;
 };
 
 // rest: 4 corners TL,TR,BL,BR of the rest cell (integer valued), stab: the stabilized corners already
@@ -301,6 +302,9 @@ MF_HD void cell_setup(const double* rest, const double* stab, int W, int H, Cell
   out.fhi_x = (float)(Rr - L) + 31.5f / 32.0f;
   out.fhi_y = (float)(B - T) + 31.5f / 32.0f;
   out.feps = -1.0f;
+  out.bounded = ((pos || neg) && finite) ? 1 : 0;
+  out.pad2_ = 0;
+  out.pad_[0] = out.pad_[1] = 0.0f;
   if ((pos || neg) && finite) {
     double fx0 = floor(x0) - 2.0, fx1 = ceil(x1) + 2.0, fy0 = floor(y0) - 2.0, fy1 = ceil(y1) + 2.0;
     fx0 = fx0 < 0.0 ? 0.0 : fx0; fy0 = fy0 < 0.0 ? 0.0 : fy0;
@@ -534,6 +538,315 @@ MF_HD int resize_blend(int p00, int p01, int p10, int p11, int a0, int a1, int b
   const int s1 = a0 * p10 + a1 * p11;
   int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
   return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fast path of the warp (warp_fast.cuh): exact row spans per cell + float32 remap coordinates with a
+// proven rounding band.
+//
+// (1) Row spans.  For a cell whose membership denominator keeps one sign over its support box, the
+//     test cell_inside() is, in real arithmetic, four half-planes alpha*x + beta*y + gamma >= 0 in
+//     output-pixel coordinates: X >= lo_x  <=>  32*NX - (lo_x - 1/2)*D >= 0 (D > 0), etc.  On one
+//     output row the member pixels are therefore one interval [a, b].  span_of_row() finds it from
+//     the half-planes and settles the (at most one per half-plane) pixel that lies within the
+//     rounding noise of a boundary with the exact test, so the interval equals cell_inside() pixel
+//     for pixel.  "noise" bounds |reference float64 evaluation - real arithmetic| with a 32x margin.
+// (2) Float32 remap coordinates.  U = 32*(map_x - L0), V = 32*(map_y - T0) evaluated in float32 in
+//     box-local coordinates differ from the real-arithmetic value by less than eps (derivation in
+//     DESIGN.md section 4); when U is farther than eps from a rounding boundary (k + 1/2), rint(U) is
+//     the reference's rint(32 * float32(map_x)) - 32*L0 exactly: rounding to float32 is monotone and
+//     every tie (k + 1/2)/32 is a float32 (|map| < 2^17), so float32(map_x) stays on its side of the
+//     tie -- unless map_x is within half a float32 ulp of it, where it can land ON the tie and
+//     round-half-even decides; that radius (16 ulp of the largest |map| of the cell, in 1/32-px
+//     units) is part of the band.  Pixels inside the band take the float64 path.
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) CellFast {
+  float a[9];          // U = (a0 x' + a1 y' + a2) / (a6 x' + a7 y' + a8), V = (a3 x' + a4 y' + a5) / (same); a8 == 1
+  float thr_u;         // a pixel is safe when |U - rint(U)| <= thr_u and |V - rint(V)| <= thr_v; thr_u < 0: no fast path
+  int bx0, by0;        // x' = px - bx0, y' = py - by0
+  int base_x, base_y;  // 32*L0, 32*T0: source 1/32-px coordinate = base + rint(U)
+  unsigned flags;      // kEdge*: pixels of this cell can satisfy a crop-edge search (mfs.py:1075-1098)
+  float thr_v;
+};
+
+struct alignas(16) CellSpan {
+  double al[4], be[4], ga[4];   // half-planes, already multiplied by the sign of the denominator
+  double noise;                 // |evaluated half-plane - truth| bound
+  int regular;                  // 1: spans are valid; 0: resolve this cell pixel by pixel
+  int pad_;
+};
+
+static constexpr unsigned kEdgeLeft = 1u, kEdgeRight = 2u, kEdgeTop = 4u, kEdgeBottom = 8u;
+static constexpr unsigned kSegNone = 0xffffu;    // no cell covers the segment: default map, border colour
+static constexpr unsigned kSegIrregular = 0xfffeu;  // resolve every pixel of this row segment exactly
+static constexpr unsigned kSegSentinel = 0xffffffffu;
+static constexpr int kSegMax = 16;
+
+// rest rectangle bounds L, Rr, T, B as cell_setup computes them (floor/ceil of the rest corners)
+MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, int H, CellFast& cf, CellSpan& sp) {
+  for (int i = 0; i < 9; ++i) cf.a[i] = 0.0f;
+  cf.thr_u = cf.thr_v = -1.0f; cf.bx0 = c.bx0; cf.by0 = c.by0;
+  const int L0 = L - 1, T0 = T - 1;
+  cf.base_x = 32 * L0; cf.base_y = 32 * T0;
+  cf.flags = (L <= 2 ? kEdgeLeft : 0u) | (Rr >= W - 3 ? kEdgeRight : 0u) | (T <= 2 ? kEdgeTop : 0u) |
+             (B >= H - 3 ? kEdgeBottom : 0u);
+  for (int i = 0; i < 4; ++i) { sp.al[i] = sp.be[i] = sp.ga[i] = 0.0; }
+  sp.noise = 0.0; sp.regular = 0; sp.pad_ = 0;
+  if (!c.bounded || c.bx0 > c.bx1) return;
+  const double fx0 = (double)c.bx0, fx1 = (double)c.bx1, fy0 = (double)c.by0, fy1 = (double)c.by1;
+  const double cx[4] = {fx0, fx1, fx0, fx1}, cy[4] = {fy0, fy0, fy1, fy1};
+  // ---- spans: membership half-planes ----
+  {
+    const double* M = c.Mi;
+    bool dpos = true, dneg = true, fin = true;
+    double dmin = 1e300, dmax = 0.0;
+    for (int i = 0; i < 4; ++i) {
+      const double d = M[6] * cx[i] + M[7] * cy[i] + M[8];
+      dpos = dpos && d > 0.0; dneg = dneg && d < 0.0;
+      const double a = fabs(d);
+      dmin = a < dmin ? a : dmin; dmax = a > dmax ? a : dmax;
+    }
+    for (int i = 0; i < 9; ++i) fin = fin && (fabs(M[i]) < 1e100);
+    if ((dpos || dneg) && fin && dmin > 1e-100 && dmax < 1e100) {
+      const double sg = dpos ? 1.0 : -1.0;
+      const double kx0 = (double)c.lo_x - 0.5, kx1 = (double)c.hi_x + 0.5;
+      const double ky0 = (double)c.lo_y - 0.5, ky1 = (double)c.hi_y + 0.5;
+      sp.al[0] = sg * (32.0 * M[0] - kx0 * M[6]); sp.be[0] = sg * (32.0 * M[1] - kx0 * M[7]); sp.ga[0] = sg * (32.0 * M[2] - kx0 * M[8]);
+      sp.al[1] = sg * (kx1 * M[6] - 32.0 * M[0]); sp.be[1] = sg * (kx1 * M[7] - 32.0 * M[1]); sp.ga[1] = sg * (kx1 * M[8] - 32.0 * M[2]);
+      sp.al[2] = sg * (32.0 * M[3] - ky0 * M[6]); sp.be[2] = sg * (32.0 * M[4] - ky0 * M[7]); sp.ga[2] = sg * (32.0 * M[5] - ky0 * M[8]);
+      sp.al[3] = sg * (ky1 * M[6] - 32.0 * M[3]); sp.be[3] = sg * (ky1 * M[7] - 32.0 * M[4]); sp.ga[3] = sg * (ky1 * M[8] - 32.0 * M[5]);
+      const double w = (double)W, h = (double)H;
+      const double magD = fabs(M[6]) * w + fabs(M[7]) * h + fabs(M[8]);
+      const double magX = fabs(M[0]) * w + fabs(M[1]) * h + fabs(M[2]);
+      const double magY = fabs(M[3]) * w + fabs(M[4]) * h + fabs(M[5]);
+      const double magN = magX > magY ? magX : magY;
+      const double kmax = 32.0 * (w + h) + 64.0;          // |lo|, |hi| + 1/2 never exceed this
+      const double u48 = 3.5527136788005009e-15;          // 2^-48: 32x the rounding unit times the ~6 roundings involved
+      const double ref = u48 * (32.0 * magN / dmin + kmax * (magD / dmin + 1.0));   // reference X, Y vs truth (1/32-px units)
+      sp.noise = 2.0 * (ref * dmax + u48 * (32.0 * magN + kmax * magD));
+      sp.regular = 1;
+    }
+  }
+  // ---- float32 remap coordinates in box-local form ----
+  {
+    const double* h = c.Hsu;
+    const double d0 = h[6] * fx0 + h[7] * fy0 + 1.0;
+    bool dpos = true, dneg = true;
+    double dmin = 1e300, dmax = 0.0;
+    for (int i = 0; i < 4; ++i) {
+      const double d = h[6] * cx[i] + h[7] * cy[i] + 1.0;
+      dpos = dpos && d > 0.0; dneg = dneg && d < 0.0;
+      const double a = fabs(d);
+      dmin = a < dmin ? a : dmin; dmax = a > dmax ? a : dmax;
+    }
+    if (!((dpos || dneg) && dmin >= 0.5 * dmax && dmin > 1e-100 && dmax < 1e100)) return;
+    const double l0 = (double)L0, t0 = (double)T0;
+    double l[9] = {32.0 * (h[0] - l0 * h[6]), 32.0 * (h[1] - l0 * h[7]), 32.0 * ((h[0] * fx0 + h[1] * fy0 + h[2]) - l0 * d0),
+                   32.0 * (h[3] - t0 * h[6]), 32.0 * (h[4] - t0 * h[7]), 32.0 * ((h[3] * fx0 + h[4] * fy0 + h[5]) - t0 * d0),
+                   h[6], h[7], d0};
+    for (int i = 0; i < 9; ++i) l[i] /= d0;
+    const double bw = fx1 - fx0, bh = fy1 - fy0;
+    const double su = fabs(l[0]) * bw + fabs(l[1]) * bh + fabs(l[2]);
+    const double sv = fabs(l[3]) * bw + fabs(l[4]) * bh + fabs(l[5]);
+    const double sd = fabs(l[6]) * bw + fabs(l[7]) * bh + 1.0;
+    const double umax = 32.0 * (double)((Rr - L > B - T ? Rr - L : B - T) + 3);
+    const double dn = dmin / fabs(d0);
+    const double u24 = 5.9604644775390625e-08;             // 2^-24
+    const double eps = u24 * (4.0 * (su > sv ? su : sv) + 8.0 * umax * sd) / dn + 1e-5;
+    // half a float32 ulp of the absolute coordinate, in 1/32-px units: 16 * 2^(e-23), |coordinate| < 2^(e+1)
+    double tie_u = 16.0 * 1.1920928955078125e-07, tie_v = tie_u;
+    const double xm = (double)((L0 < 0 ? -L0 : L0) > Rr + 2 ? (L0 < 0 ? -L0 : L0) : Rr + 2) + 1.0;
+    const double ym = (double)((T0 < 0 ? -T0 : T0) > B + 2 ? (T0 < 0 ? -T0 : T0) : B + 2) + 1.0;
+    for (double p = 1.0; p < xm; p *= 2.0) tie_u *= 2.0;
+    for (double p = 1.0; p < ym; p *= 2.0) tie_v *= 2.0;
+    if (!(eps + tie_u < 0.2) || !(eps + tie_v < 0.2) || !(su < 1e6) || !(sv < 1e6) || !(xm < 1e5) || !(ym < 1e5)) return;
+    for (int i = 0; i < 9; ++i) cf.a[i] = (float)l[i];
+    cf.thr_u = (float)(0.5 - 1.001 * (eps + tie_u));
+    cf.thr_v = (float)(0.5 - 1.001 * (eps + tie_v));
+  }
+}
+
+// Member pixels of cell c on output row y within columns [xlo, xhi] (already clipped to the cell's
+// box).  Returns 0 and the inclusive interval [a, b]; 1 when no pixel is a member; 2 when the row
+// cannot be described by an interval with certainty (caller resolves it pixel by pixel).
+MF_HD int span_of_row(const Cell& c, const CellSpan& sp, int y, int xlo, int xhi, int& a, int& b) {
+  const double yd = (double)y;
+  double lo = (double)xlo, hi = (double)xhi;
+  for (int i = 0; i < 4; ++i) {
+    const double al = sp.al[i];
+    const double rowc = sp.be[i] * yd + sp.ga[i];
+    const double aal = fabs(al);
+    if (aal < 4.0 * sp.noise) {
+      // (almost) no dependence on x over any frame width the library accepts: decide the row as a whole
+      const double c0 = al * (double)xlo + rowc, c1 = al * (double)xhi + rowc;
+      const double cmin = c0 < c1 ? c0 : c1, cmax = c0 < c1 ? c1 : c0;
+      const double slack = sp.noise + aal;
+      if (cmin > slack) continue;
+      if (cmax < -slack) return 1;
+      return 2;
+    }
+    const double t = -rowc / al;
+    const double m = sp.noise / aal + 1e-7;               // < 0.26
+    if (!(t == t) || fabs(t) > 1e15) return 2;
+    if (al > 0.0) {                                        // pixels x >= t
+      double first = floor(t + m) + 1.0;                   // smallest integer certainly on the member side
+      const double p = first - 1.0;
+      if (p >= t - m && p >= lo && p <= hi && cell_inside(c, p, yd)) first = p;
+      if (first > lo) lo = first;
+    } else {                                               // pixels x <= t
+      double last = ceil(t - m) - 1.0;
+      const double p = last + 1.0;
+      if (p <= t + m && p >= lo && p <= hi && cell_inside(c, p, yd)) last = p;
+      if (last < hi) hi = last;
+    }
+    if (lo > hi) return 1;
+  }
+  a = (int)lo; b = (int)hi;
+  return 0;
+}
+
+// Row segments of one 128-pixel tile row: which cell owns each pixel ("the last cell written wins",
+// mfs.py:1060-1061).  Candidates are visited by descending id; each takes what is still uncovered
+// of its span.  seg[i] = (first x << 16) | cell id, ascending x, seg[0] starts at x0; unused entries
+// are kSegSentinel.  Returns the number of segments, or -1 when more than cap are needed.
+struct SegBuilder {
+  int ulo[8], uhi[8], nu;          // uncovered intervals
+  unsigned seg[kSegMax];
+  int ns;
+  bool overflow;
+  MF_HD void begin(int x0, int x1) { ulo[0] = x0; uhi[0] = x1; nu = 1; ns = 0; overflow = false; }
+  MF_HD void emit(int x, unsigned id, int cap) {
+    if (ns >= cap) { overflow = true; return; }
+    seg[ns++] = ((unsigned)x << 16) | id;
+  }
+  MF_HD void cover(int a, int b, unsigned id, int cap) {
+    const int n0 = nu;
+    for (int i = 0; i < n0; ++i) {
+      const int lo = a > ulo[i] ? a : ulo[i], hi = b < uhi[i] ? b : uhi[i];
+      if (lo > hi) continue;
+      emit(lo, id, cap);
+      const int olo = ulo[i], ohi = uhi[i];
+      if (lo > olo && hi < ohi) {                          // split in two
+        if (nu >= 8) { overflow = true; return; }
+        uhi[i] = lo - 1; ulo[nu] = hi + 1; uhi[nu] = ohi; ++nu;
+      } else if (lo > olo) uhi[i] = lo - 1;
+      else if (hi < ohi) ulo[i] = hi + 1;
+      else { ulo[i] = 1; uhi[i] = 0; }                     // fully covered
+    }
+  }
+  MF_HD bool done() const {
+    for (int i = 0; i < nu; ++i) if (ulo[i] <= uhi[i]) return false;
+    return true;
+  }
+  MF_HD int finish(int cap) {
+    for (int i = 0; i < nu; ++i) if (ulo[i] <= uhi[i]) emit(ulo[i], kSegNone, cap);
+    if (overflow) return -1;
+    for (int i = 1; i < ns; ++i) {                         // ascending x (high half-word)
+      const unsigned v = seg[i];
+      int j = i - 1;
+      while (j >= 0 && seg[j] > v) { seg[j + 1] = seg[j]; --j; }
+      seg[j + 1] = v;
+    }
+    return ns;
+  }
+};
+
+// Owner of pixel x in a sorted segment list (slow path; the fast path does this per 4-pixel group).
+MF_HD unsigned seg_owner(const unsigned* seg, int cap, int x) {
+  const unsigned key = ((unsigned)x << 16) | 0xffffu;
+  unsigned cur = seg[0];
+  for (int i = 1; i < cap; ++i) {
+    if (seg[i] == kSegSentinel) break;
+    if (seg[i] <= key) cur = seg[i];
+  }
+  return cur & 0xffffu;
+}
+
+static constexpr float kRoundMagic = 12582912.0f;          // 1.5 * 2^23: adding it rounds to an integer (RNE)
+static constexpr unsigned kRoundMagicBits = 0x4b400000u;
+
+// Float32 remap coordinate of one pixel: nU = rint(U) + kRoundMagicBits as raw bits; returns whether
+// the pixel is outside the rounding band (safe).  bx, by, bw: row parts a1*y'+a2, a4*y'+a5, a7*y'+a8.
+MF_HD bool fast_coords(float a0, float a3, float a6, float bx, float by, float bw, float x, float thr_u, float thr_v,
+                       unsigned& nU, unsigned& nV) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(a6, x, bw)));
+  const float U = __fmul_rn(fmaf(a0, x, bx), r), V = __fmul_rn(fmaf(a3, x, by), r);
+  const float tU = __fadd_rn(U, kRoundMagic), tV = __fadd_rn(V, kRoundMagic);
+  const float dU = __fsub_rn(U, __fsub_rn(tU, kRoundMagic)), dV = __fsub_rn(V, __fsub_rn(tV, kRoundMagic));
+  nU = __float_as_uint(tU); nV = __float_as_uint(tV);
+#else
+  const float r = 1.0f / fmaf(a6, x, bw);
+  const float U = fmaf(a0, x, bx) * r, V = fmaf(a3, x, by) * r;
+  volatile float tU = U + kRoundMagic, tV = V + kRoundMagic;
+  const float dU = U - (tU - kRoundMagic), dV = V - (tV - kRoundMagic);
+  union { float f; unsigned u; } cu, cv; cu.f = tU; cv.f = tV;
+  nU = cu.u; nV = cv.u;
+#endif
+  return fabsf(dU) <= thr_u && fabsf(dV) <= thr_v;         // NaN compares false: not safe
+}
+
+
+// One group of four adjacent output pixels (px0..px0+3, py) owned by one cell: raw rounded coordinates
+// nu[j], nv[j] (rint + kRoundMagicBits) and the mask of pixels inside the rounding band.
+MF_HD unsigned fast_group_coords(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+                                 float a8, float thr_u, float thr_v, int cbx0, int cby0, int px0, int py, unsigned* nu,
+                                 unsigned* nv) {
+  const float fy = (float)(py - cby0);
+  const float bx = fmaf(a1, fy, a2), by = fmaf(a4, fy, a5), bw = fmaf(a7, fy, a8);
+  const float fx = (float)(px0 - cbx0);
+  unsigned bad = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 4; ++j)
+    if (!fast_coords(a0, a3, a6, bx, by, bw, fx + (float)j, thr_u, thr_v, nu[j], nv[j])) bad |= 1u << j;
+  return bad;
+}
+
+MF_HD unsigned umin4(const unsigned* v) { unsigned a = v[0] < v[1] ? v[0] : v[1], b = v[2] < v[3] ? v[2] : v[3]; return a < b ? a : b; }
+MF_HD unsigned umax4(const unsigned* v) { unsigned a = v[0] > v[1] ? v[0] : v[1], b = v[2] > v[3] ? v[2] : v[3]; return a > b ? a : b; }
+
+// What to do with the group: returns the mask of pixels for the slow path (15 = the whole group) and
+// whether the group takes the shared-window gather (`fast`).  The gather needs adjacent footprints
+// (pixel j reads source columns ix0+j, ix0+j+1 of rows iy0, iy0+1), every tap -- and the 5-word row
+// reads -- inside the frame, and no pixel that could satisfy a crop-edge search (those are decided on
+// the exact float32 map; a pixel in the rounding band is off by at most one unit, hence the +-2).
+MF_HD unsigned fast_group_plan(const unsigned* nu, const unsigned* nv, unsigned bad, int base_x, int base_y,
+                               unsigned flags, int W, int H, bool bounds_only, int& ix0, int& iy0, bool& fast) {
+  const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
+  const unsigned spread = (nu[1] - bu - 32u) | (nu[2] - bu - 64u) | (nu[3] - bu - 96u) | (nv[1] - bv) | (nv[2] - bv) |
+                          (nv[3] - bv);
+  ix0 = (int)(bu - kRoundMagicBits + (unsigned)base_x) >> 5;
+  iy0 = (int)(bv - kRoundMagicBits + (unsigned)base_y) >> 5;
+  bool edge = false;
+  if (flags != 0u) {
+    const int nx_lo = (int)(umin4(nu) - kRoundMagicBits) + base_x, nx_hi = (int)(umax4(nu) - kRoundMagicBits) + base_x;
+    const int ny_lo = (int)(umin4(nv) - kRoundMagicBits) + base_y, ny_hi = (int)(umax4(nv) - kRoundMagicBits) + base_y;
+    edge = ((flags & kEdgeLeft) && nx_lo < 32 + 2) || ((flags & kEdgeRight) && nx_hi > 32 * (W - 2) - 2) ||
+           ((flags & kEdgeTop) && ny_lo < 32 + 2) || ((flags & kEdgeBottom) && ny_hi > 32 * (H - 2) - 2);
+  }
+  fast = false;
+  if (bounds_only) return edge ? 15u : 0u;
+  const bool ok = !edge && spread < 32u && ix0 >= 0 && ix0 <= W - 8 && iy0 >= 0 && iy0 <= H - 2;
+  fast = ok;
+  return ok ? bad : 15u;
+}
+
+// Owner of the group [px0, px0+3] in a sorted segment list and whether a segment starts inside it.
+MF_HD unsigned seg_group_owner(const unsigned* seg, int cap, int px0, bool& straddle) {
+  const unsigned key = ((unsigned)px0 << 16) | 0xffffu;
+  unsigned cur = seg[0];
+  straddle = false;
+  for (int i = 1; i < cap; ++i) {
+    const unsigned v = seg[i];
+    if (v == kSegSentinel) break;
+    if (v <= key) cur = v;
+    straddle = straddle || ((v - key - 1u) < 0x30000u);
+  }
+  return cur & 0xffffu;
 }
 
 }  // namespace mf

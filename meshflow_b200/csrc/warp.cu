@@ -22,6 +22,7 @@
 // HBM layout: frames [nf][H][W][3] uint8 (row pitch 3W, no padding -- BGR24 rows are multiples of 16
 // bytes at every standard resolution); cells [nf][R*C] mf::Cell (240 B); tile lists
 // [nf][tiles][kTileCap] uint16 + counts.
+#include <stdlib.h>
 #include "mf_common.cuh"
 #include "mf_math.cuh"
 
@@ -38,6 +39,7 @@ static constexpr int kWarpThreads = 256; // 32 lanes x 8 rows
 __global__ void __launch_bounds__(128) cell_setup_kernel(
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
     int nf, int W, int H, int R, int C, int tiles_x, int tiles_y, Cell* __restrict__ cells,
+    CellFast* __restrict__ fast, CellSpan* __restrict__ spans,
     int* __restrict__ tile_count, uint16_t* __restrict__ tile_list, int32_t* __restrict__ crop_out) {
   const int ncell = R * C;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,6 +68,15 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
   Cell cell;
   cell_setup(rest, stab, W, H, cell);
   cells[idx] = cell;
+  if (fast != nullptr) {                  // fast path: box-local float32 map + membership half-planes
+    CellFast cf;
+    CellSpan sp;
+    // rest corners are TL, TR, BL, BR of an axis-aligned rectangle (mfs.py:1039-1044)
+    cell_fast_setup(cell, (int)floor(fmin(rest[0], rest[4])), (int)ceil(fmax(rest[2], rest[6])),
+                    (int)floor(fmin(rest[1], rest[3])), (int)ceil(fmax(rest[5], rest[7])), W, H, cf, sp);
+    fast[idx] = cf;
+    spans[idx] = sp;
+  }
   if (cell.bx0 > cell.bx1) return;
   // Only cells whose rest rectangle reaches within two pixels of the frame border can produce remap
   // coordinates that satisfy a crop-edge search (|m - e| < 1, mfs.py:1075-1098): a pixel mapped by
@@ -448,17 +459,38 @@ struct WarpWorkspace {
   Cell* cells;
   int* tile_count;
   uint16_t* tile_list;
+  CellFast* fast;        // fast path (warp_fast.cuh)
+  CellSpan* spans;
+  uint32_t* rowseg;
+  int segcap;
 };
 
+// Segments per 128-px tile row: wide cells (16 x 16 mesh at >= 720p) need few; 16 covers 64 x 64 meshes at 720p.
+static int seg_capacity(int W, int C) { return (W / C >= 48) ? 8 : kSegMax; }
+
 static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorkspace& w) {
-  const size_t tiles = (size_t)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const size_t tiles_x = (size_t)((W + kTileW - 1) / kTileW);
+  const size_t tiles = tiles_x * ((H + kTileH - 1) / kTileH);
   w.cells = cv.take<Cell>((size_t)nf * R * C);
   w.tile_count = cv.take<int>((size_t)nf * tiles);
   w.tile_list = cv.take<uint16_t>((size_t)nf * tiles * kTileCap);
+  w.fast = cv.take<CellFast>((size_t)nf * R * C);
+  w.spans = cv.take<CellSpan>((size_t)nf * R * C);
+  w.segcap = seg_capacity(W, C);
+  w.rowseg = cv.take<uint32_t>((size_t)nf * H * tiles_x * w.segcap);
   return cv.ok();
 }
 
 }  // namespace mf
+
+#include "warp_fast.cuh"
+
+// The fast path needs cell ids below the two reserved segment owners and frames wide enough for its
+// 5-word row reads; MF_WARP_GENERIC=1 forces the generic kernel (A/B comparisons).
+static bool use_fast_path(int W, int H, int R, int C) {
+  static const bool forced_generic = [] { const char* e = getenv("MF_WARP_GENERIC"); return e && e[0] == '1'; }();
+  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && R * C < (int)mf::kSegIrregular;
+}
 
 extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {
   if (nf <= 0 || W <= 0 || H <= 0 || R <= 0 || C <= 0) return 0;
@@ -470,17 +502,30 @@ extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {
 
 // memset + cell_setup + tile_sort: everything the pixel pass and the bounds-only pass share
 static int prepare_cells(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H, int R,
-                         int C, int32_t* crop_out, const mf::WarpWorkspace& w, cudaStream_t st) {
+                         int C, int32_t* crop_out, const mf::WarpWorkspace& w, bool fast, cudaStream_t st) {
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
   cudaError_t ce = cudaMemsetAsync(w.tile_count, 0, (size_t)nf * tiles_x * tiles_y * sizeof(int), st);
   if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "warp: memset: %s", cudaGetErrorString(ce));
   const int64_t ncells = (int64_t)nf * R * C;
   mf::cell_setup_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(
-      u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, w.tile_count, w.tile_list, crop_out);
+      u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, fast ? w.fast : nullptr, fast ? w.spans : nullptr,
+      w.tile_count, w.tile_list, crop_out);
   if (int e = mf::check_launch("cell_setup")) return e;
   const int64_t ntiles = (int64_t)nf * tiles_x * tiles_y;
   mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
-  return mf::check_launch("tile_sort");
+  if (int e = mf::check_launch("tile_sort")) return e;
+  if (fast) {
+    const int64_t nrows = (int64_t)nf * H * tiles_x;
+    mf::row_segments_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
+        w.cells, w.spans, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.segcap, w.rowseg);
+    return mf::check_launch("row_segments");
+  }
+  return MF_OK;
+}
+
+static dim3 fast_grid(int nf, int W, int H) {
+  return dim3((unsigned)((W + mf::kTileW - 1) / mf::kTileW), (unsigned)((H + mf::kFastTileH - 1) / mf::kFastTileH),
+              (unsigned)nf);
 }
 
 extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W,
@@ -494,8 +539,15 @@ extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float
   if (!mf::carve_warp(cv, nf, W, H, R, C, w))
     return mf::fail(MF_E_WORKSPACE, "mf_warp_crop_bounds: workspace %zu < %zu bytes", workspace_bytes, cv.used);
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, st)) return e;
+  const bool fast = use_fast_path(W, H, R, C);
+  if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, fast, st)) return e;
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
+  if (fast) {
+    mf::warp_fast_kernel<true><<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(
+        nullptr, nullptr, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, w.segcap, crop_out, W, H, R * C, tiles_x,
+        tiles_y, 0u);
+    return mf::check_launch("warp_fast_bounds");
+  }
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
   if ((W % mf::kTileW == 0) && (H % mf::kTileH == 0))
     mf::warp_kernel<false, true, true><<<grid, mf::kWarpThreads, 0, st>>>(
@@ -522,7 +574,16 @@ extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const d
     return mf::fail(MF_E_WORKSPACE, "mf_warp_frames: workspace %zu < %zu bytes", workspace_bytes, cv.used);
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
-  if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, st)) return e;
+  // the float32 maps (map_out, parity checks only) exist in the generic kernel alone
+  const bool fast = map_out == nullptr && use_fast_path(W, H, R, C);
+  if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, fast, st)) return e;
+  if (fast) {
+    const uint32_t border = (uint32_t)(border_b & 255) | ((uint32_t)(border_g & 255) << 8) | ((uint32_t)(border_r & 255) << 16);
+    mf::warp_fast_kernel<false><<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(
+        frames_in, frames_out, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, w.segcap, crop_out, W, H, R * C,
+        tiles_x, tiles_y, border);
+    return mf::check_launch("warp_fast");
+  }
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
   const bool full = (W % mf::kTileW == 0) && (H % mf::kTileH == 0);
 #define MF_LAUNCH_WARP(MAPS, FULL)                                                                        \

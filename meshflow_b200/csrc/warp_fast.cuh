@@ -1,0 +1,288 @@
+// Fast path of the mesh warp (included by warp.cu).
+//
+// The generic kernel (warp_kernel) decides, for every group of four pixels, which cell owns it by
+// screening candidates, and evaluates the reference's float64 remap sequence for every pixel: about
+// 190 instructions per pixel, issue-bound at 10 % of the HBM roofline.  The fast path moves every
+// decision that does not depend on pixel data out of the pixel loop:
+//
+//   row_segments_kernel : one thread per (frame, row, 128-px tile): exact member interval of every
+//                         candidate cell on that row (span_of_row: four half-planes + the exact test
+//                         for a pixel within rounding noise of a boundary), resolved by "the last cell
+//                         written wins" into <= 16 sorted segments (first x, cell id).
+//   warp_fast_kernel    : CTA = 128 x 40 output pixels, warp = 128 x 5, four adjacent pixels per thread
+//                         and row.  Per row a thread looks its cell up in the segment list, evaluates
+//                         the cell's remap coordinates in float32 in box-local form (error < eps, see
+//                         mf_math.cuh) and keeps rint() only when the value is outside the rounding
+//                         band; the four footprints are adjacent, so the two source rows are read once
+//                         as 4-5 aligned words each, brought to phase 0 with funnel shifts, and the
+//                         taps are regrouped with constant-selector PRMTs for the dp2a blend.
+//                         Everything else -- pixels inside the rounding band, groups that straddle a
+//                         segment, non-adjacent footprints, taps outside the frame, crop-edge
+//                         candidates, irregular cells -- is appended to a shared-memory queue and
+//                         handled after a barrier by slow_pixel(): the reference's float64 sequence,
+//                         pixel by pixel, with all lanes busy.
+//
+// Results are identical to warp_kernel (tests/test_gpu_parity.py compares both with the oracle).
+#pragma once
+
+namespace mf {
+
+static constexpr int kFastRows = 5;                          // rows per warp
+static constexpr int kFastTileH = 8 * kFastRows;             // 40: divides 720, 1080, 1440, 2160, 4320
+static constexpr int kQueueCap = kTileW * kFastTileH;        // every pixel of the tile fits: no overflow path
+
+__global__ void __launch_bounds__(128) row_segments_kernel(
+    const Cell* __restrict__ cells, const CellSpan* __restrict__ spans, const int* __restrict__ tile_count,
+    const uint16_t* __restrict__ tile_list, int nf, int W, int H, int ncell, int tiles_x, int tiles_y, int segcap,
+    uint32_t* __restrict__ rowseg) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)nf * H * tiles_x;
+  if (idx >= total) return;
+  const int tx = (int)(idx % tiles_x);
+  const int64_t fy = idx / tiles_x;
+  const int y = (int)(fy % H), f = (int)(fy / H);
+  const int x0 = tx * kTileW, x1 = min(W - 1, x0 + kTileW - 1);
+  const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(y / kTileH) * tiles_x + tx;
+  const int nraw = __ldg(tile_count + tile) & kCountMask;
+  uint32_t* out = rowseg + (size_t)idx * segcap;
+  SegBuilder sb;
+  sb.begin(x0, x1);
+  bool irregular = nraw > kTileCap;
+  const Cell* fcells = cells + (size_t)f * ncell;
+  const CellSpan* fspans = spans + (size_t)f * ncell;
+  const uint16_t* list = tile_list + tile * kTileCap;       // sorted by descending id
+  for (int k = 0; k < nraw && !irregular; ++k) {
+    const int id = __ldg(list + k);
+    const Cell& c = fcells[id];
+    const int4 box = __ldg(reinterpret_cast<const int4*>(&c));
+    if (y < box.y || y > box.w || x1 < box.x || x0 > box.z) continue;
+    const CellSpan& sp = fspans[id];
+    if (!sp.regular) { irregular = true; break; }
+    int a, b;
+    const int st = span_of_row(c, sp, y, max(x0, box.x), min(x1, box.z), a, b);
+    if (st == 2) { irregular = true; break; }
+    if (st == 0) sb.cover(a, b, (unsigned)id, segcap);
+    if (sb.overflow) { irregular = true; break; }
+    if (sb.done()) break;
+  }
+  int ns = irregular ? -1 : sb.finish(segcap);
+  if (ns < 0) {
+    out[0] = ((unsigned)x0 << 16) | kSegIrregular;
+    for (int i = 1; i < segcap; ++i) out[i] = kSegSentinel;
+  } else {
+    for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : kSegSentinel;
+  }
+}
+
+// One pixel the slow way: owner from the segment list (or the exact per-pixel search for irregular
+// segments), the reference's float64 remap sequence, the four crop-edge searches, the general tap
+// fetch with the constant border.
+__device__ __noinline__ void slow_pixel(int px, int py, int f, const uint8_t* __restrict__ src,
+                                        uint8_t* __restrict__ dst_frame, const Cell* __restrict__ fcells,
+                                        const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
+                                        const uint32_t* __restrict__ rowseg, int segcap, int32_t* __restrict__ crop_out,
+                                        int W, int H, int ncell, int tiles_x, int tiles_y, uint32_t border) {
+  const int tx = px / kTileW;
+  const uint32_t* rs = rowseg + (((size_t)f * H + py) * tiles_x + tx) * segcap;
+  const unsigned id = seg_owner(rs, segcap, px);
+  float mx = (float)(W + 1), my = (float)(H + 1);           // mfs.py:983-984
+  if (id == kSegIrregular) {
+    const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
+    const int nraw = __ldg(tile_count + tile) & kCountMask;
+    const bool overflow = nraw > kTileCap;
+    const float2 m = resolve_pixel(fcells, overflow ? nullptr : tile_list + tile * kTileCap, overflow ? ncell : nraw,
+                                   px, py, mx, my);
+    mx = m.x; my = m.y;
+  } else if (id != kSegNone) {
+    const double2* hs = reinterpret_cast<const double2*>(fcells[id].Hsu);
+    const double2 h01 = __ldg(hs), h23 = __ldg(hs + 1), h45 = __ldg(hs + 2), h67 = __ldg(hs + 3);
+    const double y = (double)py;
+    map_row(h01.x, h23.x, h23.y, h45.y, h67.x, (double)px, MF_MUL(y, h01.y), MF_MUL(y, h45.x), MF_MUL(y, h67.y), mx, my);
+  }
+  int32_t* cr = crop_out + 4 * f;                           // mfs.py:1075-1098; plain read first: most hits do not improve
+  if (mx > -1.0f && mx < 1.0f && px > cr[0]) atomicMax(cr + 0, px);
+  if (my > -1.0f && my < 1.0f && py > cr[1]) atomicMax(cr + 1, py);
+  if (mx > (float)(W - 2) && mx < (float)W && px < cr[2]) atomicMin(cr + 2, px);
+  if (my > (float)(H - 2) && my < (float)H && py < cr[3]) atomicMin(cr + 3, py);
+  if (dst_frame == nullptr) return;
+  int ix, iy, ax, ay;
+  remap_coords(mx, my, ix, iy, ax, ay);
+  uint32_t o;
+  if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
+    o = blend_interior(src, W * 3, ix, iy, ax, ay);
+  } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {
+    o = border;
+  } else {
+    uint8_t t3[3];
+    remap_pixel(src, W, H, ix, iy, ax, ay, (int)(border & 0xffu), (int)((border >> 8) & 0xffu), (int)((border >> 16) & 0xffu), t3);
+    o = (uint32_t)t3[0] | ((uint32_t)t3[1] << 8) | ((uint32_t)t3[2] << 16);
+  }
+  uint8_t* d = dst_frame + ((size_t)py * W + px) * 3;
+  d[0] = (uint8_t)(o & 0xffu); d[1] = (uint8_t)((o >> 8) & 0xffu); d[2] = (uint8_t)((o >> 16) & 0xffu);
+}
+
+// (B, G) pairs and R pair of pixel J of a group from the phase-0 words s0..s3 of one source row:
+// bytes (3J, 3J+3), (3J+1, 3J+4) and (3J+2, 3J+5) of the row segment.
+template <int J>
+__device__ __forceinline__ void tap_pairs(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t& bg, uint32_t& r) {
+  if (J == 0) { bg = __byte_perm(s0, s1, 0x4130); r = __byte_perm(s0, s1, 0x0052); }
+  if (J == 1) { bg = __byte_perm(s0, s1, 0x7463); r = __byte_perm(s1, s2, 0x0041); }
+  if (J == 2) { bg = __byte_perm(s1, s2, 0x6352); r = __byte_perm(s2, s2, 0x0030); }
+  if (J == 3) { bg = __byte_perm(s2, s3, 0x5241); r = __byte_perm(s2, s3, 0x0063); }
+}
+
+// cv2.remap's blend of pixel J: (sum w_rc p_rc + 512) >> 10 with w_rc = wy_r * wx_c
+template <int J>
+__device__ __forceinline__ void blend_group_pixel(const uint32_t (&st)[4], const uint32_t (&sb)[4], unsigned ax, unsigned ay,
+                                                  uint32_t& vb, uint32_t& vg, uint32_t& vr) {
+  uint32_t tbg, tr, bbg, br;
+  tap_pairs<J>(st[0], st[1], st[2], st[3], tbg, tr);
+  tap_pairs<J>(sb[0], sb[1], sb[2], sb[3], bbg, br);
+  const uint32_t wxp = ax * 0xffffu + 32u;                  // (32 - ax) | ax << 16
+  const uint32_t wb = wxp * ay, wa = (wxp << 5) - wb;       // rows: ay, 32 - ay
+  vb = __dp2a_lo(wb, bbg, __dp2a_lo(wa, tbg, 512u)) >> 10;
+  vg = __dp2a_hi(wb, bbg, __dp2a_hi(wa, tbg, 512u)) >> 10;
+  vr = __dp2a_lo(wb, br, __dp2a_lo(wa, tr, 512u)) >> 10;
+}
+
+template <bool kBoundsOnly>
+__global__ void __launch_bounds__(kWarpThreads, 3) warp_fast_kernel(
+    const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, const Cell* __restrict__ cells,
+    const CellFast* __restrict__ fast, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
+    const uint32_t* __restrict__ rowseg, int segcap, int32_t* __restrict__ crop_out, int W, int H, int ncell,
+    int tiles_x, int tiles_y, uint32_t border) {
+  __shared__ uint32_t queue[kQueueCap];
+  __shared__ int qn;
+  const int f = blockIdx.z, tx = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) qn = 0;
+  __syncthreads();
+  const int px0 = tx * kTileW + lane * kPix;
+  const int y_first = blockIdx.y * kFastTileH + warp * kFastRows;
+  const int npx = min(kPix, W - px0);                        // <= 0: this lane has no pixels
+  const uint8_t* src = frames_in + (size_t)f * H * W * 3;
+  uint8_t* dstf = kBoundsOnly ? nullptr : frames_out + (size_t)f * H * W * 3;
+  const Cell* fcells = cells + (size_t)f * ncell;
+  const CellFast* ffast = fast + (size_t)f * ncell;
+  const unsigned pitch = (unsigned)W * 3u;
+  const bool word_store = ((pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(dstf) & 3u) == 0u);
+  const uint32_t key = ((uint32_t)px0 << 16) | 0xffffu;
+
+  unsigned cur_id = 0xffffffffu;
+  float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, thr = -1.0f, thr_v = -1.0f;
+  int cbx0 = 0, cby0 = 0, base_x = 0, base_y = 0;
+  unsigned flags = 0;
+
+#pragma unroll 1
+  for (int r = 0; r < kFastRows; ++r) {
+    const int py = y_first + r;
+    if (py >= H) break;
+    if (npx <= 0) continue;
+    if (kBoundsOnly) {                                       // only tiles that hold a border cell can produce a hit
+      const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
+      if (!(__ldg(tile_count + tile) & kEdgeFlag)) continue;
+    }
+    // ---- owner of the group from the row's segment list ----
+    const uint32_t* rs = rowseg + (((size_t)f * H + py) * tiles_x + tx) * segcap;
+    uint4 e = __ldg(reinterpret_cast<const uint4*>(rs));
+    uint32_t cur = e.x;
+    bool strad = false;
+#define MF_SEG_STEP(v) { if ((v) <= key) cur = (v); strad = strad || (((v) - key - 1u) < 0x30000u); }
+    if (e.y != kSegSentinel) {
+      MF_SEG_STEP(e.y);
+      if (e.z != kSegSentinel) {
+        MF_SEG_STEP(e.z);
+        if (e.w != kSegSentinel) {
+          MF_SEG_STEP(e.w);
+          for (int q = 4; q < segcap; q += 4) {
+            e = __ldg(reinterpret_cast<const uint4*>(rs + q));
+            if (e.x == kSegSentinel) break;
+            MF_SEG_STEP(e.x); MF_SEG_STEP(e.y); MF_SEG_STEP(e.z); MF_SEG_STEP(e.w);
+          }
+        }
+      }
+    }
+#undef MF_SEG_STEP
+    const unsigned id = cur & 0xffffu;
+    unsigned push = 0u;                                      // bit j: pixel j goes to the slow queue
+    bool fast_group = false;
+    unsigned nu[kPix], nv[kPix];
+    int ix0 = 0, iy0 = 0;
+    if (strad || id == kSegIrregular || npx < kPix) {
+      push = (1u << npx) - 1u;
+    } else if (id == kSegNone) {
+      if (!kBoundsOnly) {                                    // no cell: map (W+1, H+1), border colour, no crop hit
+        uint32_t o[kPix] = {border, border, border, border};
+        store_bgr4(dstf + ((size_t)py * W + px0) * 3, o, kPix, word_store);
+      }
+    } else {
+      if (id != cur_id) {
+        const float4* cp = reinterpret_cast<const float4*>(ffast + id);
+        const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
+        const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
+        a0 = q0.x; a1 = q0.y; a2 = q0.z; a3 = q0.w; a4 = q1.x; a5 = q1.y; a6 = q1.z; a7 = q1.w; a8 = q2.x; thr = q2.y;
+        cbx0 = __float_as_int(q2.z); cby0 = __float_as_int(q2.w);
+        base_x = q3.x; base_y = q3.y; flags = (unsigned)q3.z; thr_v = __int_as_float(q3.w);
+        cur_id = id;
+      }
+      if (thr < 0.0f) {
+        push = 15u;
+      } else {
+        const unsigned bad = fast_group_coords(a0, a1, a2, a3, a4, a5, a6, a7, a8, thr, thr_v, cbx0, cby0, px0, py, nu, nv);
+        push = fast_group_plan(nu, nv, bad, base_x, base_y, flags, W, H, kBoundsOnly, ix0, iy0, fast_group);
+      }
+    }
+    if (push != 0u) {
+      const int n = __popc(push);
+      int slot = atomicAdd(&qn, n);
+#pragma unroll
+      for (int j = 0; j < kPix; ++j)
+        if (push & (1u << j)) queue[slot++] = (uint32_t)(px0 + j) | ((uint32_t)py << 16);
+    }
+    if (!kBoundsOnly && fast_group) {
+      const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
+      const uintptr_t p0 = reinterpret_cast<uintptr_t>(src) + (unsigned)iy0 * pitch + (unsigned)ix0 * 3u;
+      const uintptr_t p1 = p0 + pitch;
+      const unsigned f0 = (unsigned)(p0 & 3u), f1 = (unsigned)(p1 & 3u);
+      const uint32_t* w0 = reinterpret_cast<const uint32_t*>(p0 & ~(uintptr_t)3);
+      const uint32_t* w1 = reinterpret_cast<const uint32_t*>(p1 & ~(uintptr_t)3);
+      uint32_t t[5], b[5];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { t[i] = __ldg(w0 + i); b[i] = __ldg(w1 + i); }
+      t[4] = f0 >= 2u ? __ldg(w0 + 4) : 0u;
+      b[4] = f1 >= 2u ? __ldg(w1 + 4) : 0u;
+      uint32_t st[4], sb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        st[i] = __funnelshift_r(t[i], t[i + 1], f0 * 8u);
+        sb[i] = __funnelshift_r(b[i], b[i + 1], f1 * 8u);
+      }
+      uint32_t vb[kPix], vg[kPix], vr[kPix];
+      const unsigned ay0 = nv[0] - bv;
+      blend_group_pixel<0>(st, sb, nu[0] - bu, ay0, vb[0], vg[0], vr[0]);
+      blend_group_pixel<1>(st, sb, nu[1] - bu - 32u, nv[1] - bv, vb[1], vg[1], vr[1]);
+      blend_group_pixel<2>(st, sb, nu[2] - bu - 64u, nv[2] - bv, vb[2], vg[2], vr[2]);
+      blend_group_pixel<3>(st, sb, nu[3] - bu - 96u, nv[3] - bv, vb[3], vg[3], vr[3]);
+      uint8_t* d = dstf + ((size_t)py * W + px0) * 3;
+      if (word_store) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+        __stcs(d32 + 0, __byte_perm(__byte_perm(vb[0], vg[0], 0x0040), __byte_perm(vr[0], vb[1], 0x0040), 0x5410));
+        __stcs(d32 + 1, __byte_perm(__byte_perm(vg[1], vr[1], 0x0040), __byte_perm(vb[2], vg[2], 0x0040), 0x5410));
+        __stcs(d32 + 2, __byte_perm(__byte_perm(vr[2], vb[3], 0x0040), __byte_perm(vg[3], vr[3], 0x0040), 0x5410));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kPix; ++j) { d[3 * j] = (uint8_t)vb[j]; d[3 * j + 1] = (uint8_t)vg[j]; d[3 * j + 2] = (uint8_t)vr[j]; }
+      }
+    }
+  }
+  // ---- everything the fast path declined, all lanes busy ----
+  __syncthreads();
+  const int n = qn;
+  for (int i = tid; i < n; i += kWarpThreads) {
+    const uint32_t q = queue[i];
+    slow_pixel((int)(q & 0xffffu), (int)(q >> 16), f, src, dstf, fcells, tile_count, tile_list, rowseg, segcap, crop_out,
+               W, H, ncell, tiles_x, tiles_y, border);
+  }
+}
+
+}  // namespace mf

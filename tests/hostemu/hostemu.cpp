@@ -7,6 +7,9 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include <algorithm>
+#include <cmath>
+#include <utility>
 #include "../../meshflow_b200/csrc/mf_math.cuh"
 
 extern "C" {
@@ -131,6 +134,180 @@ void emu_crop_resize(const uint8_t* src, int W, int H, int left, int top, int ri
         dst[((size_t)y * W + x) * 3 + ch] = (uint8_t)mf::resize_blend(
             p0[(left + x0[x]) * 3 + ch], p0[(left + x1[x]) * 3 + ch], p1[(left + x0[x]) * 3 + ch],
             p1[(left + x1[x]) * 3 + ch], a0[x], a1[x], b0, b1);
+  }
+}
+
+
+// ---- fast path of the warp (meshflow_b200/csrc/warp_fast.cuh), same decisions on the CPU -----------
+static void emu_cells_all(const float* vertex_xy, const double* u, const double* s, int W, int H, int R, int C,
+                          std::vector<mf::Cell>& cells, std::vector<mf::CellFast>& fast, std::vector<mf::CellSpan>& spans) {
+  cells.resize(R * C); fast.resize(R * C); spans.resize(R * C);
+  for (int r = 0; r < R; ++r)
+    for (int c = 0; c < C; ++c) {
+      const int vidx[4] = {r * (C + 1) + c, r * (C + 1) + c + 1, (r + 1) * (C + 1) + c, (r + 1) * (C + 1) + c + 1};
+      double rest[8], stab[8];
+      for (int k = 0; k < 4; ++k)
+        for (int d = 0; d < 2; ++d) {
+          const int v = vidx[k];
+          const double rv = (double)vertex_xy[2 * v + d];
+          rest[2 * k + d] = rv;
+          stab[2 * k + d] = (double)(float)(rv + (s[2 * v + d] - u[2 * v + d]));
+        }
+      const int id = r * C + c;
+      mf::cell_setup(rest, stab, W, H, cells[id]);
+      mf::cell_fast_setup(cells[id], (int)floor(fmin(rest[0], rest[4])), (int)ceil(fmax(rest[2], rest[6])),
+                          (int)floor(fmin(rest[1], rest[3])), (int)ceil(fmax(rest[5], rest[7])), W, H, fast[id], spans[id]);
+    }
+}
+
+// Every (cell, row) span against the exact membership test, pixel by pixel over the cell's box.
+// out[0] = rows examined, out[1] = rows span_of_row declined (status 2), out[2] = pixels where the span
+// disagrees with cell_inside (must be 0), out[3] = regular cells.
+void emu_span_audit(const float* vertex_xy, const double* u, const double* s, int W, int H, int R, int C, long long* out) {
+  std::vector<mf::Cell> cells; std::vector<mf::CellFast> fast; std::vector<mf::CellSpan> spans;
+  emu_cells_all(vertex_xy, u, s, W, H, R, C, cells, fast, spans);
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (int id = 0; id < R * C; ++id) {
+    const mf::Cell& c = cells[id];
+    if (!spans[id].regular) continue;
+    out[3]++;
+    for (int y = c.by0; y <= c.by1; ++y) {
+      int a = 1, b = 0;
+      const int st = mf::span_of_row(c, spans[id], y, c.bx0, c.bx1, a, b);
+      out[0]++;
+      if (st == 2) { out[1]++; continue; }
+      if (st == 1) { a = 1; b = 0; }
+      for (int x = c.bx0; x <= c.bx1; ++x)
+        if (mf::cell_inside(c, (double)x, (double)y) != (x >= a && x <= b)) out[2]++;
+    }
+    // rows outside the box hold no member pixel (the box is a superset of the mask)
+  }
+}
+
+// stats: [0] pixels through the shared-window gather, [1] slow pixels, [2] pixels in the rounding band,
+// [3] irregular row segments, [4] row segments, [5] groups sent whole to the slow path
+void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const double* u, const double* s, int W, int H,
+                         int R, int C, int bb, int bg, int br, uint8_t* dst, int* crop4, int bounds_only, long long* stats) {
+  const int kTileW = 128, kTileH = 8, kTileCap = 48;
+  std::vector<mf::Cell> cells; std::vector<mf::CellFast> fast; std::vector<mf::CellSpan> spans;
+  emu_cells_all(vertex_xy, u, s, W, H, R, C, cells, fast, spans);
+  const int ncell = R * C, tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+  const int segcap = (W / C >= 48) ? 8 : mf::kSegMax;
+  std::vector<std::vector<int>> lists(tiles_x * tiles_y);
+  for (int id = ncell - 1; id >= 0; --id) {                 // descending id
+    const mf::Cell& c = cells[id];
+    if (c.bx0 > c.bx1) continue;
+    for (int ty = c.by0 / kTileH; ty <= c.by1 / kTileH; ++ty)
+      for (int tx = c.bx0 / kTileW; tx <= c.bx1 / kTileW; ++tx) lists[ty * tiles_x + tx].push_back(id);
+  }
+  std::vector<unsigned> rowseg((size_t)H * tiles_x * segcap);
+  for (int i = 0; i < 6; ++i) stats[i] = 0;
+  for (int y = 0; y < H; ++y)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      const std::vector<int>& l = lists[(y / kTileH) * tiles_x + tx];
+      const int x0 = tx * kTileW, x1 = std::min(W - 1, x0 + kTileW - 1);
+      mf::SegBuilder sb; sb.begin(x0, x1);
+      bool irregular = (int)l.size() > kTileCap;
+      for (size_t k = 0; k < l.size() && !irregular; ++k) {
+        const int id = l[k];
+        const mf::Cell& c = cells[id];
+        if (y < c.by0 || y > c.by1 || x1 < c.bx0 || x0 > c.bx1) continue;
+        if (!spans[id].regular) { irregular = true; break; }
+        int a, b;
+        const int st = mf::span_of_row(c, spans[id], y, std::max(x0, c.bx0), std::min(x1, c.bx1), a, b);
+        if (st == 2) { irregular = true; break; }
+        if (st == 0) sb.cover(a, b, (unsigned)id, segcap);
+        if (sb.overflow) { irregular = true; break; }
+        if (sb.done()) break;
+      }
+      const int ns = irregular ? -1 : sb.finish(segcap);
+      unsigned* out = &rowseg[((size_t)y * tiles_x + tx) * segcap];
+      stats[4]++;
+      if (ns < 0) { out[0] = ((unsigned)x0 << 16) | mf::kSegIrregular; for (int i = 1; i < segcap; ++i) out[i] = mf::kSegSentinel; stats[3]++; }
+      else for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : mf::kSegSentinel;
+    }
+  int crop[4] = {0, 0, W - 1, H - 1};
+  std::vector<std::pair<int, int>> queue;
+  const int bord[3] = {bb, bg, br};
+  for (int py = 0; py < H; ++py)
+    for (int px0 = 0; px0 < W; px0 += 4) {
+      const int npx = std::min(4, W - px0), tx = px0 / kTileW;
+      if (bounds_only) {
+        bool edge_tile = false;
+        for (int id : lists[(py / kTileH) * tiles_x + tx]) {
+          const mf::CellFast& cf = fast[id];
+          edge_tile = edge_tile || cf.flags != 0u;          // superset of the kernel's tile flag
+        }
+        if (!edge_tile) continue;
+      }
+      const unsigned* rs = &rowseg[((size_t)py * tiles_x + tx) * segcap];
+      bool strad;
+      const unsigned id = mf::seg_group_owner(rs, segcap, px0, strad);
+      unsigned push = 0u; bool fg = false; unsigned nu[4], nv[4]; int ix0 = 0, iy0 = 0;
+      if (strad || id == mf::kSegIrregular || npx < 4) push = (1u << npx) - 1u;
+      else if (id == mf::kSegNone) {
+        if (!bounds_only) for (int j = 0; j < 4; ++j) for (int ch = 0; ch < 3; ++ch) dst[((size_t)py * W + px0 + j) * 3 + ch] = (uint8_t)bord[ch];
+      } else {
+        const mf::CellFast& cf = fast[id];
+        if (cf.thr_u < 0.0f) push = 15u;
+        else {
+          const unsigned bad = mf::fast_group_coords(cf.a[0], cf.a[1], cf.a[2], cf.a[3], cf.a[4], cf.a[5], cf.a[6], cf.a[7],
+                                                     cf.a[8], cf.thr_u, cf.thr_v, cf.bx0, cf.by0, px0, py, nu, nv);
+          stats[2] += __builtin_popcount(bad);
+          push = mf::fast_group_plan(nu, nv, bad, cf.base_x, cf.base_y, cf.flags, W, H, bounds_only != 0, ix0, iy0, fg);
+        }
+      }
+      if (push == 15u || (npx < 4 && push)) stats[5]++;
+      for (int j = 0; j < 4; ++j) if (push & (1u << j)) queue.push_back({px0 + j, py});
+      if (fg && !bounds_only) {
+        const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
+        for (int j = 0; j < 4; ++j) {
+          const int ax = (int)(nu[j] - bu) - 32 * j, ay = (int)(nv[j] - bv);
+          const uint8_t* r0 = src + ((size_t)iy0 * W + ix0 + j) * 3;
+          const uint8_t* r1 = r0 + (size_t)W * 3;
+          for (int ch = 0; ch < 3; ++ch)
+            dst[((size_t)py * W + px0 + j) * 3 + ch] = (uint8_t)mf::blend4(r0[ch], r0[3 + ch], r1[ch], r1[3 + ch], ax, ay);
+        }
+        stats[0] += 4;
+      }
+    }
+  stats[1] = (long long)queue.size();
+  for (auto& q : queue) {
+    const int px = q.first, py = q.second, tx = px / kTileW;
+    const unsigned id = mf::seg_owner(&rowseg[((size_t)py * tiles_x + tx) * segcap], segcap, px);
+    float mx = (float)(W + 1), my = (float)(H + 1);
+    if (id == mf::kSegIrregular) {
+      const std::vector<int>& l = lists[(py / kTileH) * tiles_x + tx];
+      const bool overflow = (int)l.size() > kTileCap;
+      const int n = overflow ? ncell : (int)l.size();
+      for (int k = 0; k < n; ++k) {
+        const mf::Cell& c = cells[overflow ? ncell - 1 - k : l[k]];
+        if (px < c.bx0 || px > c.bx1 || py < c.by0 || py > c.by1) continue;
+        if (mf::cell_inside(c, (double)px, (double)py)) { mf::cell_map(c, (double)px, (double)py, mx, my); break; }
+      }
+    } else if (id != mf::kSegNone) {
+      mf::cell_map(cells[id], (double)px, (double)py, mx, my);
+    }
+    if (mx > -1.0f && mx < 1.0f && px > crop[0]) crop[0] = px;
+    if (my > -1.0f && my < 1.0f && py > crop[1]) crop[1] = py;
+    if (mx > (float)(W - 2) && mx < (float)W && px < crop[2]) crop[2] = px;
+    if (my > (float)(H - 2) && my < (float)H && py < crop[3]) crop[3] = py;
+    if (bounds_only) continue;
+    int ix, iy, ax, ay;
+    mf::remap_coords(mx, my, ix, iy, ax, ay);
+    mf::remap_pixel(src, W, H, ix, iy, ax, ay, bb, bg, br, dst + ((size_t)py * W + px) * 3);
+  }
+  for (int i = 0; i < 4; ++i) crop4[i] = crop[i];
+}
+
+
+// per cell: out[6*id..] = regular, bounded, thr_u, thr_v, box width, box height
+void emu_cell_fast_info(const float* vertex_xy, const double* u, const double* s, int W, int H, int R, int C, double* out) {
+  std::vector<mf::Cell> cells; std::vector<mf::CellFast> fast; std::vector<mf::CellSpan> spans;
+  emu_cells_all(vertex_xy, u, s, W, H, R, C, cells, fast, spans);
+  for (int id = 0; id < R * C; ++id) {
+    out[6 * id] = spans[id].regular; out[6 * id + 1] = cells[id].bounded; out[6 * id + 2] = fast[id].thr_u;
+    out[6 * id + 3] = fast[id].thr_v; out[6 * id + 4] = cells[id].bx1 - cells[id].bx0 + 1; out[6 * id + 5] = cells[id].by1 - cells[id].by0 + 1;
   }
 }
 

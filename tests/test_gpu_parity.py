@@ -160,6 +160,12 @@ def test_warp_matches_oracle(W, H, R, C, F, amp):
         assert np.array_equal(maps[f, :, :, 1], ref_maps[f][1])
         assert np.array_equal(out[f], ref_frames[f]), f"{(out[f] != ref_frames[f]).sum()} samples differ"
         assert crop[f].tolist() == ref_pf[f].tolist()
+    # production path (no maps requested): row segments + float32 coordinates outside the rounding band
+    out_fast, crop_fast = core.warp_frames(_dev(frames, core), _dev(u, core), _dev(s, core))
+    out_fast = out_fast.cpu().numpy(); crop_fast = crop_fast.cpu().numpy()
+    for f in range(F):
+        assert np.array_equal(out_fast[f], ref_frames[f]), f"fast path: {(out_fast[f] != ref_frames[f]).any(axis=2).sum()} px differ"
+        assert crop_fast[f].tolist() == ref_pf[f].tolist()
     enc = core.combine_crop(torch.from_numpy(crop).to(core.device))
     assert core.decode_crop(enc) == tuple(ref_crop)
     bounds = core.warp_crop_bounds(_dev(u, core), _dev(s, core)).cpu().numpy()       # pass A: no pixels read
@@ -169,6 +175,31 @@ def test_warp_matches_oracle(W, H, R, C, F, amp):
         b = core.crop_resize(torch.from_numpy(out).to(core.device), ref_crop).cpu().numpy()
         assert np.array_equal(a, b)
         assert np.array_equal(a[0], spec.resize_fixed(out[0][ref_crop[1]:ref_crop[3] + 1, ref_crop[0]:ref_crop[2] + 1], W, H))
+
+
+@pytest.mark.parametrize("W,H,R,C", [(1920, 1080, 16, 16), (1280, 720, 64, 64), (1000, 562, 16, 16), (3840, 2160, 32, 32)])
+def test_warp_fast_path_equals_generic_kernel_on_camera_like_warps(W, H, R, C):
+    """Smooth (rotation / scale / perspective) warps as a stabilizer produces them: the production kernel
+    (shared-window gather for almost every group) against the generic kernel, whole frames, bit for bit."""
+    rng = np.random.default_rng(W + C)
+    F = 3
+    frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+    rest = spec.vertex_xy(W, H, R, C).astype(np.float64)
+    d = np.zeros((F, (R + 1) * (C + 1), 2))
+    for f in range(F):
+        Hm = synth.random_homography(rng, W, H, rot=0.004 * (1 + 3 * f), scale=0.003 * (1 + 3 * f), trans=4.0 * (1 + f))
+        w = rest[:, 0] * Hm[2, 0] + rest[:, 1] * Hm[2, 1] + 1.0
+        d[f, :, 0] = (rest[:, 0] * Hm[0, 0] + rest[:, 1] * Hm[0, 1] + Hm[0, 2]) / w - rest[:, 0]
+        d[f, :, 1] = (rest[:, 0] * Hm[1, 0] + rest[:, 1] * Hm[1, 1] + Hm[1, 2]) / w - rest[:, 1]
+    d += rng.normal(0, 0.1, d.shape)
+    u = np.zeros((F, R + 1, C + 1, 2)); s = d.reshape(F, R + 1, C + 1, 2)
+    core = _core(W, H, R, C, border_bgr=(1, 2, 3))
+    fd = _dev(frames, core)
+    gen, crop_gen, _ = core.warp_frames(fd, _dev(u, core), _dev(s, core), return_maps=True)
+    fast, crop_fast = core.warp_frames(fd, _dev(u, core), _dev(s, core))
+    assert torch.equal(gen, fast), f"{(gen != fast).any(dim=3).sum().item()} px differ"
+    assert torch.equal(crop_gen, crop_fast)
+    assert torch.equal(core.warp_crop_bounds(_dev(u, core), _dev(s, core)), crop_gen)
 
 
 def test_warp_identity_is_a_copy():

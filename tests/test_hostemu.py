@@ -104,3 +104,86 @@ def test_warp_arithmetic_matches_spec(emu, W, H, R, C, amp, seed):
         l, t, r, b = (int(v) for v in crop)
         emu.emu_crop_resize(P(dst), W, H, l, t, r, b, P(out))
         assert np.array_equal(out, spec.resize_fixed(dst[t:b + 1, l:r + 1], W, H))
+
+
+# ----------------------------------------------------------------------------------------------
+# fast path of the warp (csrc/warp_fast.cuh): exact row spans + float32 coordinates outside the band
+# ----------------------------------------------------------------------------------------------
+FAST_CASES = [(320, 180, 8, 8, 2.5, 1), (200, 120, 4, 6, 15.0, 3), (256, 144, 16, 16, 1.0, 5), (640, 360, 16, 16, 3.0, 7),
+              (333, 217, 6, 9, 2.0, 9), (640, 360, 40, 40, 0.8, 11)]
+
+
+@pytest.mark.parametrize("W,H,R,C,amp,seed", FAST_CASES)
+def test_row_spans_equal_the_membership_test_pixel_for_pixel(emu, W, H, R, C, amp, seed):
+    rng = np.random.default_rng(seed)
+    _, u, s = synth.synthetic_warp_inputs(rng, 1, W, H, R, C, per_vertex=amp, per_frame=1.2 * amp)
+    rest = spec.vertex_xy(W, H, R, C)
+    uu = np.ascontiguousarray(u[0].reshape(-1, 2)); ss = np.ascontiguousarray(s[0].reshape(-1, 2))
+    audit = np.zeros(4, np.int64)
+    emu.emu_span_audit(P(rest), P(uu), P(ss), W, H, R, C, P(audit))
+    assert audit[2] == 0, "a row span disagrees with cell_inside"
+    assert audit[1] == 0 or amp > 5
+    if amp < 5:
+        assert audit[3] >= 0.95 * R * C
+
+
+@pytest.mark.parametrize("W,H,R,C,amp,seed", FAST_CASES)
+def test_fast_warp_path_matches_spec(emu, W, H, R, C, amp, seed):
+    rng = np.random.default_rng(seed)
+    frames, u, s = synth.synthetic_warp_inputs(rng, 1, W, H, R, C, per_vertex=amp, per_frame=1.2 * amp)
+    rest = spec.vertex_xy(W, H, R, C)
+    uu = np.ascontiguousarray(u[0].reshape(-1, 2)); ss = np.ascontiguousarray(s[0].reshape(-1, 2))
+    src = np.ascontiguousarray(frames[0])
+    dst = np.zeros((H, W, 3), np.uint8); crop = np.zeros(4, np.int32); stats = np.zeros(6, np.int64)
+    emu.emu_warp_frame_fast(P(src), P(rest), P(uu), P(ss), W, H, R, C, 9, 8, 7, P(dst), P(crop), 0, P(stats))
+    sc = spec.cell_setup(rest, ss - uu, R, C)
+    mx, my, _ = spec.warp_maps(W, H, sc, prune=False)
+    ref = spec.remap_fixed(src, mx, my, (9, 8, 7))
+    assert np.array_equal(dst, ref), f"{(dst != ref).any(axis=2).sum()} pixels differ; stats {stats.tolist()}"
+    assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
+    crop2 = np.zeros(4, np.int32); stats2 = np.zeros(6, np.int64)
+    emu.emu_warp_frame_fast(P(src), P(rest), P(uu), P(ss), W, H, R, C, 9, 8, 7, None, P(crop2), 1, P(stats2))
+    assert crop2.tolist() == crop.tolist()
+    if amp < 3:
+        assert stats[3] <= 0.01 * stats[4]           # (almost) no irregular row segments on mild meshes
+
+
+def test_fast_warp_path_takes_most_pixels_of_a_smooth_warp(emu):
+    """Camera-like warp (small rotation / scale / translation, as in configs[1]): nearly every group of
+    four pixels has adjacent footprints and takes the shared-window gather."""
+    W, H, R, C = 640, 360, 16, 16
+    rng = np.random.default_rng(33)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    rest = spec.vertex_xy(W, H, R, C).astype(np.float64)
+    Hm = synth.random_homography(rng, W, H, rot=0.004, scale=0.003, trans=4.0)
+    w = rest[:, 0] * Hm[2, 0] + rest[:, 1] * Hm[2, 1] + 1.0
+    moved = np.stack([(rest[:, 0] * Hm[0, 0] + rest[:, 1] * Hm[0, 1] + Hm[0, 2]) / w,
+                      (rest[:, 0] * Hm[1, 0] + rest[:, 1] * Hm[1, 1] + Hm[1, 2]) / w], axis=1)
+    d = np.ascontiguousarray(moved - rest + rng.normal(0, 0.05, rest.shape))
+    zero = np.zeros_like(d)
+    dst = np.zeros_like(src); crop = np.zeros(4, np.int32); stats = np.zeros(6, np.int64)
+    emu.emu_warp_frame_fast(P(src), P(spec.vertex_xy(W, H, R, C)), P(zero), P(d), W, H, R, C, 0, 0, 255, P(dst), P(crop), 0, P(stats))
+    sc = spec.cell_setup(spec.vertex_xy(W, H, R, C), d, R, C)
+    mx, my, _ = spec.warp_maps(W, H, sc, prune=False)
+    assert np.array_equal(dst, spec.remap_fixed(src, mx, my, (0, 0, 255)))
+    assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
+    assert stats[0] > 0.85 * W * H, f"fast path took only {stats[0]} of {W * H} pixels: {stats.tolist()}"
+
+
+def test_fast_warp_path_identity_and_folded_mesh(emu):
+    W, H, R, C = 256, 144, 8, 8
+    rng = np.random.default_rng(21)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    rest = spec.vertex_xy(W, H, R, C)
+    zero = np.zeros(((R + 1) * (C + 1), 2))
+    dst = np.zeros_like(src); crop = np.zeros(4, np.int32); stats = np.zeros(6, np.int64)
+    emu.emu_warp_frame_fast(P(src), P(rest), P(zero), P(zero), W, H, R, C, 0, 0, 255, P(dst), P(crop), 0, P(stats))
+    assert np.array_equal(dst, src) and crop.tolist() == [0, 0, W - 1, H - 1]
+    # a folded mesh: one vertex pulled across its neighbours (cells overlap, some are not convex)
+    d = rng.normal(0, 2.0, ((R + 1) * (C + 1), 2))
+    d[4 * (C + 1) + 4] += (70.0, 45.0)
+    emu.emu_warp_frame_fast(P(src), P(rest), P(zero), P(np.ascontiguousarray(d)), W, H, R, C, 0, 0, 255, P(dst), P(crop), 0, P(stats))
+    sc = spec.cell_setup(rest, d, R, C)
+    mx, my, _ = spec.warp_maps(W, H, sc, prune=False)
+    assert np.array_equal(dst, spec.remap_fixed(src, mx, my, (0, 0, 255)))
+    assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
