@@ -552,8 +552,8 @@ MF_HD int resize_blend(int p00, int p01, int p10, int p11, int a0, int a1, int b
 //     the half-planes and settles the (at most one per half-plane) pixel that lies within the
 //     rounding noise of a boundary with the exact test, so the interval equals cell_inside() pixel
 //     for pixel.  "noise" bounds |reference float64 evaluation - real arithmetic| with a 32x margin.
-// (2) Float32 remap coordinates.  U = 32*(map_x - L0), V = 32*(map_y - T0) evaluated in float32 in
-//     box-local coordinates differ from the real-arithmetic value by less than eps (derivation in
+// (2) Float32 remap coordinates.  U = 32*(map_x - X0), V = 32*(map_y - Y0) evaluated in float32 in
+//     box-centred coordinates differ from the real-arithmetic value by less than eps (derivation in
 //     DESIGN.md section 4); when U is farther than eps from a rounding boundary (k + 1/2), rint(U) is
 //     the reference's rint(32 * float32(map_x)) - 32*L0 exactly: rounding to float32 is monotone and
 //     every tie (k + 1/2)/32 is a float32 (|map| < 2^17), so float32(map_x) stays on its side of the
@@ -564,8 +564,8 @@ MF_HD int resize_blend(int p00, int p01, int p10, int p11, int a0, int a1, int b
 struct alignas(16) CellFast {
   float a[9];          // U = (a0 x' + a1 y' + a2) / (a6 x' + a7 y' + a8), V = (a3 x' + a4 y' + a5) / (same); a8 == 1
   float thr_u;         // a pixel is safe when |U - rint(U)| <= thr_u and |V - rint(V)| <= thr_v; thr_u < 0: no fast path
-  int bx0, by0;        // x' = px - bx0, y' = py - by0
-  int base_x, base_y;  // 32*L0, 32*T0: source 1/32-px coordinate = base + rint(U)
+  int bx0, by0;        // x' = px - bx0, y' = py - by0 (centre of the support box)
+  int base_x, base_y;  // 32 * centre of the rest cell: source 1/32-px coordinate = base + rint(U)
   unsigned flags;      // kEdge*: pixels of this cell can satisfy a crop-edge search (mfs.py:1075-1098)
   float thr_v;
 };
@@ -587,8 +587,7 @@ static constexpr int kSegMax = 16;
 MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, int H, CellFast& cf, CellSpan& sp) {
   for (int i = 0; i < 9; ++i) cf.a[i] = 0.0f;
   cf.thr_u = cf.thr_v = -1.0f; cf.bx0 = c.bx0; cf.by0 = c.by0;
-  const int L0 = L - 1, T0 = T - 1;
-  cf.base_x = 32 * L0; cf.base_y = 32 * T0;
+  cf.base_x = cf.base_y = 0;
   cf.flags = (L <= 2 ? kEdgeLeft : 0u) | (Rr >= W - 3 ? kEdgeRight : 0u) | (T <= 2 ? kEdgeTop : 0u) |
              (B >= H - 3 ? kEdgeBottom : 0u);
   for (int i = 0; i < 4; ++i) { sp.al[i] = sp.be[i] = sp.ga[i] = 0.0; }
@@ -628,10 +627,14 @@ MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, in
       sp.regular = 1;
     }
   }
-  // ---- float32 remap coordinates in box-local form ----
+  // ---- float32 remap coordinates, centred on the box / on the rest cell (halves every magnitude) ----
   {
     const double* h = c.Hsu;
-    const double d0 = h[6] * fx0 + h[7] * fy0 + 1.0;
+    const int ocx = (c.bx0 + c.bx1) >> 1, ocy = (c.by0 + c.by1) >> 1;      // output-space origin
+    const int scx = (L + Rr) >> 1, scy = (T + B) >> 1;                     // source-space origin
+    cf.bx0 = ocx; cf.by0 = ocy; cf.base_x = 32 * scx; cf.base_y = 32 * scy;
+    const double ox = (double)ocx, oy = (double)ocy;
+    const double d0 = h[6] * ox + h[7] * oy + 1.0;
     bool dpos = true, dneg = true;
     double dmin = 1e300, dmax = 0.0;
     for (int i = 0; i < 4; ++i) {
@@ -641,25 +644,27 @@ MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, in
       dmin = a < dmin ? a : dmin; dmax = a > dmax ? a : dmax;
     }
     if (!((dpos || dneg) && dmin >= 0.5 * dmax && dmin > 1e-100 && dmax < 1e100)) return;
-    const double l0 = (double)L0, t0 = (double)T0;
-    double l[9] = {32.0 * (h[0] - l0 * h[6]), 32.0 * (h[1] - l0 * h[7]), 32.0 * ((h[0] * fx0 + h[1] * fy0 + h[2]) - l0 * d0),
-                   32.0 * (h[3] - t0 * h[6]), 32.0 * (h[4] - t0 * h[7]), 32.0 * ((h[3] * fx0 + h[4] * fy0 + h[5]) - t0 * d0),
+    const double l0 = (double)scx, t0 = (double)scy;
+    double l[9] = {32.0 * (h[0] - l0 * h[6]), 32.0 * (h[1] - l0 * h[7]), 32.0 * ((h[0] * ox + h[1] * oy + h[2]) - l0 * d0),
+                   32.0 * (h[3] - t0 * h[6]), 32.0 * (h[4] - t0 * h[7]), 32.0 * ((h[3] * ox + h[4] * oy + h[5]) - t0 * d0),
                    h[6], h[7], d0};
     for (int i = 0; i < 9; ++i) l[i] /= d0;
-    const double bw = fx1 - fx0, bh = fy1 - fy0;
+    const double bw = (fx1 - fx0) * 0.5 + 1.0, bh = (fy1 - fy0) * 0.5 + 1.0;   // |x'|, |y'| over the box
     const double su = fabs(l[0]) * bw + fabs(l[1]) * bh + fabs(l[2]);
     const double sv = fabs(l[3]) * bw + fabs(l[4]) * bh + fabs(l[5]);
     const double sd = fabs(l[6]) * bw + fabs(l[7]) * bh + 1.0;
-    const double umax = 32.0 * (double)((Rr - L > B - T ? Rr - L : B - T) + 3);
+    // member pixels map to [L - 1, Rr + 1] x [T - 1, B + 1]: |U|, |V| <= 32 * (half extent + 2)
+    const double umax = 32.0 * (double)(((Rr - L > B - T ? Rr - L : B - T) + 1) / 2 + 2);
     const double dn = dmin / fabs(d0);
     const double u24 = 5.9604644775390625e-08;             // 2^-24
     const double eps = u24 * (4.0 * (su > sv ? su : sv) + 8.0 * umax * sd) / dn + 1e-5;
-    // half a float32 ulp of the absolute coordinate, in 1/32-px units: 16 * 2^(e-23), |coordinate| < 2^(e+1)
+    // half a float32 ulp of the absolute coordinate, in 1/32-px units: 16 * 2^(e-23) for |coordinate| < 2^(e+1)
     double tie_u = 16.0 * 1.1920928955078125e-07, tie_v = tie_u;
-    const double xm = (double)((L0 < 0 ? -L0 : L0) > Rr + 2 ? (L0 < 0 ? -L0 : L0) : Rr + 2) + 1.0;
-    const double ym = (double)((T0 < 0 ? -T0 : T0) > B + 2 ? (T0 < 0 ? -T0 : T0) : B + 2) + 1.0;
-    for (double p = 1.0; p < xm; p *= 2.0) tie_u *= 2.0;
-    for (double p = 1.0; p < ym; p *= 2.0) tie_v *= 2.0;
+    const int al = L - 1 < 0 ? 1 - L : L - 1, at = T - 1 < 0 ? 1 - T : T - 1;
+    const double xm = (double)(al > Rr + 1 ? al : Rr + 1) + 1.0;
+    const double ym = (double)(at > B + 1 ? at : B + 1) + 1.0;
+    for (double p = 2.0; p <= xm; p *= 2.0) tie_u *= 2.0;
+    for (double p = 2.0; p <= ym; p *= 2.0) tie_v *= 2.0;
     if (!(eps + tie_u < 0.2) || !(eps + tie_v < 0.2) || !(su < 1e6) || !(sv < 1e6) || !(xm < 1e5) || !(ym < 1e5)) return;
     for (int i = 0; i < 9; ++i) cf.a[i] = (float)l[i];
     cf.thr_u = (float)(0.5 - 1.001 * (eps + tie_u));
@@ -815,13 +820,13 @@ MF_HD unsigned umax4(const unsigned* v) { unsigned a = v[0] > v[1] ? v[0] : v[1]
 // reads -- inside the frame, and no pixel that could satisfy a crop-edge search (those are decided on
 // the exact float32 map; a pixel in the rounding band is off by at most one unit, hence the +-2).
 MF_HD unsigned fast_group_plan(const unsigned* nu, const unsigned* nv, unsigned bad, int base_x, int base_y,
-                               unsigned flags, int W, int H, bool bounds_only, int& ix0, int& iy0, bool& fast) {
+                               unsigned flags, int W, int H, bool bounds_only, int& ix0, int& iy0, bool& fast, bool& edge) {
   const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
   const unsigned spread = (nu[1] - bu - 32u) | (nu[2] - bu - 64u) | (nu[3] - bu - 96u) | (nv[1] - bv) | (nv[2] - bv) |
                           (nv[3] - bv);
   ix0 = (int)(bu - kRoundMagicBits + (unsigned)base_x) >> 5;
   iy0 = (int)(bv - kRoundMagicBits + (unsigned)base_y) >> 5;
-  bool edge = false;
+  edge = false;
   if (flags != 0u) {
     const int nx_lo = (int)(umin4(nu) - kRoundMagicBits) + base_x, nx_hi = (int)(umax4(nu) - kRoundMagicBits) + base_x;
     const int ny_lo = (int)(umin4(nv) - kRoundMagicBits) + base_y, ny_hi = (int)(umax4(nv) - kRoundMagicBits) + base_y;

@@ -35,6 +35,8 @@ static constexpr int kTileCap = 48;      // candidate cells per tile before the 
 static constexpr int kCountMask = 0xffff; // tile_count: low 16 bits = candidates, bit 16 = has a border cell
 static constexpr int kEdgeFlag = 0x10000;
 static constexpr int kWarpThreads = 256; // 32 lanes x 8 rows
+static constexpr int kFastRows = 5;      // fast path: rows per warp
+static constexpr int kFastTileH = 8 * kFastRows;   // 40: divides 720, 1080, 1440, 2160, 4320
 
 __global__ void __launch_bounds__(128) cell_setup_kernel(
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
@@ -489,7 +491,7 @@ static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorks
 // 5-word row reads; MF_WARP_GENERIC=1 forces the generic kernel (A/B comparisons).
 static bool use_fast_path(int W, int H, int R, int C) {
   static const bool forced_generic = [] { const char* e = getenv("MF_WARP_GENERIC"); return e && e[0] == '1'; }();
-  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && R * C < (int)mf::kSegIrregular;
+  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && (int64_t)R * C < (int64_t)mf::kSegIrregular;
 }
 
 extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {

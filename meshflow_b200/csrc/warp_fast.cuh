@@ -18,18 +18,15 @@
 //                         taps are regrouped with constant-selector PRMTs for the dp2a blend.
 //                         Everything else -- pixels inside the rounding band, groups that straddle a
 //                         segment, non-adjacent footprints, taps outside the frame, crop-edge
-//                         candidates, irregular cells -- is appended to a shared-memory queue and
-//                         handled after a barrier by slow_pixel(): the reference's float64 sequence,
-//                         pixel by pixel, with all lanes busy.
+//                         candidates, irregular cells -- is listed in the warp's shared-memory queue and
+//                         handled by the same warp right after its rows, lanes packed: medium_pixel()
+//                         (float32 coordinate, per-pixel tap fetch) for pixels that only failed a group
+//                         condition, slow_pixel() (the reference's float64 sequence) for the rest.
 //
 // Results are identical to warp_kernel (tests/test_gpu_parity.py compares both with the oracle).
 #pragma once
 
 namespace mf {
-
-static constexpr int kFastRows = 5;                          // rows per warp
-static constexpr int kFastTileH = 8 * kFastRows;             // 40: divides 720, 1080, 1440, 2160, 4320
-static constexpr int kQueueCap = kTileW * kFastTileH;        // every pixel of the tile fits: no overflow path
 
 __global__ void __launch_bounds__(128) row_segments_kernel(
     const Cell* __restrict__ cells, const CellSpan* __restrict__ spans, const int* __restrict__ tile_count,
@@ -74,17 +71,79 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   }
 }
 
-// One pixel the slow way: owner from the segment list (or the exact per-pixel search for irregular
-// segments), the reference's float64 remap sequence, the four crop-edge searches, the general tap
-// fetch with the constant border.
+// Tap fetch + blend + 3-byte store of one pixel from its 1/32-px source coordinate.
+__device__ __forceinline__ void remap_store_pixel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst_frame, int px,
+                                                  int py, int W, int H, int ix, int iy, int ax, int ay, uint32_t border) {
+  uint32_t o;
+  if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
+    o = blend_interior(src, W * 3, ix, iy, ax, ay);
+  } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {
+    o = border;
+  } else {
+    uint8_t t3[3];
+    remap_pixel(src, W, H, ix, iy, ax, ay, (int)(border & 0xffu), (int)((border >> 8) & 0xffu), (int)((border >> 16) & 0xffu), t3);
+    o = (uint32_t)t3[0] | ((uint32_t)t3[1] << 8) | ((uint32_t)t3[2] << 16);
+  }
+  uint8_t* d = dst_frame + ((size_t)py * W + px) * 3;
+  d[0] = (uint8_t)(o & 0xffu); d[1] = (uint8_t)((o >> 8) & 0xffu); d[2] = (uint8_t)((o >> 16) & 0xffu);
+}
+
+// Owner of one pixel from its row's segment list.
+__device__ __forceinline__ unsigned pixel_owner(const uint32_t* __restrict__ rs, int segcap, int px) {
+  const uint4 e = __ldg(reinterpret_cast<const uint4*>(rs));
+  const unsigned key = ((unsigned)px << 16) | 0xffffu;
+  unsigned cur = e.x;
+  if (e.y <= key) cur = e.y;                                 // sentinels never compare <= key
+  if (e.z <= key) cur = e.z;
+  if (e.w <= key) cur = e.w;
+  return e.w != kSegSentinel ? seg_owner(rs, segcap, px) : (cur & 0xffffu);
+}
+
+// One pixel that only failed a GROUP condition (the group straddles two cells, footprints not
+// adjacent, taps near the frame border): the float32 coordinate of the pixel's own cell is still exact
+// outside the rounding band, only the tap fetch is per pixel.  Returns false -- nothing written -- when
+// the pixel needs the float64 sequence after all (inside the band, crop-edge candidate, cell without
+// float32 form, irregular segment).
+__device__ __forceinline__ bool medium_pixel(int px, int py, unsigned id, const uint8_t* __restrict__ src,
+                                             uint8_t* __restrict__ dst_frame, const CellFast* __restrict__ ffast, int W,
+                                             int H, uint32_t border) {
+  if (id == kSegIrregular) return false;
+  if (id == kSegNone) {                                      // default map (W+1, H+1): border colour, no crop hit
+    if (dst_frame != nullptr) {
+      uint8_t* d = dst_frame + ((size_t)py * W + px) * 3;
+      d[0] = (uint8_t)(border & 0xffu); d[1] = (uint8_t)((border >> 8) & 0xffu); d[2] = (uint8_t)((border >> 16) & 0xffu);
+    }
+    return true;
+  }
+  const float4* cp = reinterpret_cast<const float4*>(ffast + id);
+  const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
+  const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
+  if (!(q2.y >= 0.0f)) return false;
+  const float fy = (float)(py - __float_as_int(q2.w)), fx = (float)(px - __float_as_int(q2.z));
+  unsigned nu, nv;
+  if (!fast_coords(q0.x, q0.w, q1.z, fmaf(q0.y, fy, q0.z), fmaf(q1.x, fy, q1.y), fmaf(q1.w, fy, q2.x), fx, q2.y,
+                   __int_as_float(q3.w), nu, nv))
+    return false;
+  const int sx = (int)(nu - kRoundMagicBits) + q3.x, sy = (int)(nv - kRoundMagicBits) + q3.y;
+  const unsigned flags = (unsigned)q3.z;
+  if (flags != 0u && (((flags & kEdgeLeft) && sx < 32 + 2) || ((flags & kEdgeRight) && sx > 32 * (W - 2) - 2) ||
+                      ((flags & kEdgeTop) && sy < 32 + 2) || ((flags & kEdgeBottom) && sy > 32 * (H - 2) - 2)))
+    return false;
+  if (dst_frame != nullptr) remap_store_pixel(src, dst_frame, px, py, W, H, sx >> 5, sy >> 5, sx & 31, sy & 31, border);
+  return true;
+}
+
+// One pixel the exact way: owner from the segment list (or the per-pixel search for irregular segments),
+// the reference's float64 remap sequence, the four crop-edge searches, the general tap fetch.
 __device__ __noinline__ void slow_pixel(int px, int py, int f, const uint8_t* __restrict__ src,
                                         uint8_t* __restrict__ dst_frame, const Cell* __restrict__ fcells,
-                                        const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
-                                        const uint32_t* __restrict__ rowseg, int segcap, int32_t* __restrict__ crop_out,
-                                        int W, int H, int ncell, int tiles_x, int tiles_y, uint32_t border) {
+                                        const int* __restrict__ tile_count,
+                                        const uint16_t* __restrict__ tile_list, const uint32_t* __restrict__ rowseg,
+                                        int segcap, int32_t* __restrict__ crop_out, int W, int H, int ncell, int tiles_x,
+                                        int tiles_y, uint32_t border) {
   const int tx = px / kTileW;
   const uint32_t* rs = rowseg + (((size_t)f * H + py) * tiles_x + tx) * segcap;
-  const unsigned id = seg_owner(rs, segcap, px);
+  const unsigned id = pixel_owner(rs, segcap, px);
   float mx = (float)(W + 1), my = (float)(H + 1);           // mfs.py:983-984
   if (id == kSegIrregular) {
     const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
@@ -107,18 +166,7 @@ __device__ __noinline__ void slow_pixel(int px, int py, int f, const uint8_t* __
   if (dst_frame == nullptr) return;
   int ix, iy, ax, ay;
   remap_coords(mx, my, ix, iy, ax, ay);
-  uint32_t o;
-  if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
-    o = blend_interior(src, W * 3, ix, iy, ax, ay);
-  } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {
-    o = border;
-  } else {
-    uint8_t t3[3];
-    remap_pixel(src, W, H, ix, iy, ax, ay, (int)(border & 0xffu), (int)((border >> 8) & 0xffu), (int)((border >> 16) & 0xffu), t3);
-    o = (uint32_t)t3[0] | ((uint32_t)t3[1] << 8) | ((uint32_t)t3[2] << 16);
-  }
-  uint8_t* d = dst_frame + ((size_t)py * W + px) * 3;
-  d[0] = (uint8_t)(o & 0xffu); d[1] = (uint8_t)((o >> 8) & 0xffu); d[2] = (uint8_t)((o >> 16) & 0xffu);
+  remap_store_pixel(src, dst_frame, px, py, W, H, ix, iy, ax, ay, border);
 }
 
 // (B, G) pairs and R pair of pixel J of a group from the phase-0 words s0..s3 of one source row:
@@ -145,46 +193,55 @@ __device__ __forceinline__ void blend_group_pixel(const uint32_t (&st)[4], const
   vr = __dp2a_lo(wb, br, __dp2a_lo(wa, tr, 512u)) >> 10;
 }
 
+#ifndef MF_FAST_MINBLOCKS
+#define MF_FAST_MINBLOCKS 4
+#endif
 template <bool kBoundsOnly>
-__global__ void __launch_bounds__(kWarpThreads, 3) warp_fast_kernel(
+__global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_kernel(
     const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, const Cell* __restrict__ cells,
     const CellFast* __restrict__ fast, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
     const uint32_t* __restrict__ rowseg, int segcap, int32_t* __restrict__ crop_out, int W, int H, int ncell,
     int tiles_x, int tiles_y, uint32_t border) {
-  __shared__ uint32_t queue[kQueueCap];
-  __shared__ int qn;
+  // every pixel of a warp fits, twice (a pixel whose per-pixel tap fetch fails is listed again for the float64 path)
+  __shared__ uint16_t warp_queue[kWarpThreads / 32][2 * kTileW * kFastRows];
   const int f = blockIdx.z, tx = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) qn = 0;
-  __syncthreads();
   const int px0 = tx * kTileW + lane * kPix;
   const int y_first = blockIdx.y * kFastTileH + warp * kFastRows;
   const int npx = min(kPix, W - px0);                        // <= 0: this lane has no pixels
   const uint8_t* src = frames_in + (size_t)f * H * W * 3;
   uint8_t* dstf = kBoundsOnly ? nullptr : frames_out + (size_t)f * H * W * 3;
-  const Cell* fcells = cells + (size_t)f * ncell;
   const CellFast* ffast = fast + (size_t)f * ncell;
   const unsigned pitch = (unsigned)W * 3u;
   const bool word_store = ((pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(dstf) & 3u) == 0u);
   const uint32_t key = ((uint32_t)px0 << 16) | 0xffffu;
+  // running pointers: one add per row instead of a 64-bit multiply chain
+  const size_t seg_stride = (size_t)tiles_x * segcap;
+  const uint32_t* rs = rowseg + (((size_t)f * H + y_first) * tiles_x + tx) * segcap;
+  uint8_t* drow = kBoundsOnly ? nullptr : dstf + ((size_t)y_first * W + px0) * 3;
 
   unsigned cur_id = 0xffffffffu;
   float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, thr = -1.0f, thr_v = -1.0f;
   int cbx0 = 0, cby0 = 0, base_x = 0, base_y = 0;
   unsigned flags = 0;
+  // bit 4*r + j: pixel j of row r takes the float64 path (global queue) / the per-pixel tap fetch (this warp, below)
+  unsigned exmask = 0u, medmask = 0u;
 
+  // the next row's first four segments are requested one row ahead (they come from L2)
+  uint4 e_next = make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
+  if (y_first < H && npx > 0) e_next = __ldg(reinterpret_cast<const uint4*>(rs));
 #pragma unroll 1
-  for (int r = 0; r < kFastRows; ++r) {
+  for (int r = 0; r < kFastRows; ++r, rs += seg_stride, drow += pitch) {
     const int py = y_first + r;
     if (py >= H) break;
     if (npx <= 0) continue;
+    uint4 e = e_next;
+    if (r + 1 < kFastRows && py + 1 < H) e_next = __ldg(reinterpret_cast<const uint4*>(rs + seg_stride));
     if (kBoundsOnly) {                                       // only tiles that hold a border cell can produce a hit
       const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
       if (!(__ldg(tile_count + tile) & kEdgeFlag)) continue;
     }
     // ---- owner of the group from the row's segment list ----
-    const uint32_t* rs = rowseg + (((size_t)f * H + py) * tiles_x + tx) * segcap;
-    uint4 e = __ldg(reinterpret_cast<const uint4*>(rs));
     uint32_t cur = e.x;
     bool strad = false;
 #define MF_SEG_STEP(v) { if ((v) <= key) cur = (v); strad = strad || (((v) - key - 1u) < 0x30000u); }
@@ -204,16 +261,18 @@ __global__ void __launch_bounds__(kWarpThreads, 3) warp_fast_kernel(
     }
 #undef MF_SEG_STEP
     const unsigned id = cur & 0xffffu;
-    unsigned push = 0u;                                      // bit j: pixel j goes to the slow queue
+    unsigned push = 0u, med = 0u;                            // bit j: pixel j -> float64 path / per-pixel tap fetch
     bool fast_group = false;
     unsigned nu[kPix], nv[kPix];
     int ix0 = 0, iy0 = 0;
-    if (strad || id == kSegIrregular || npx < kPix) {
+    if (id == kSegIrregular) {
       push = (1u << npx) - 1u;
+    } else if (strad || npx < kPix) {
+      med = (1u << npx) - 1u;
     } else if (id == kSegNone) {
       if (!kBoundsOnly) {                                    // no cell: map (W+1, H+1), border colour, no crop hit
         uint32_t o[kPix] = {border, border, border, border};
-        store_bgr4(dstf + ((size_t)py * W + px0) * 3, o, kPix, word_store);
+        store_bgr4(drow, o, kPix, word_store);
       }
     } else {
       if (id != cur_id) {
@@ -229,16 +288,13 @@ __global__ void __launch_bounds__(kWarpThreads, 3) warp_fast_kernel(
         push = 15u;
       } else {
         const unsigned bad = fast_group_coords(a0, a1, a2, a3, a4, a5, a6, a7, a8, thr, thr_v, cbx0, cby0, px0, py, nu, nv);
-        push = fast_group_plan(nu, nv, bad, base_x, base_y, flags, W, H, kBoundsOnly, ix0, iy0, fast_group);
+        bool edge;
+        push = fast_group_plan(nu, nv, bad, base_x, base_y, flags, W, H, kBoundsOnly, ix0, iy0, fast_group, edge);
+        if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }   // only the group shape failed
       }
     }
-    if (push != 0u) {
-      const int n = __popc(push);
-      int slot = atomicAdd(&qn, n);
-#pragma unroll
-      for (int j = 0; j < kPix; ++j)
-        if (push & (1u << j)) queue[slot++] = (uint32_t)(px0 + j) | ((uint32_t)py << 16);
-    }
+    exmask |= push << (4 * r);
+    medmask |= med << (4 * r);
     if (!kBoundsOnly && fast_group) {
       const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
       const uintptr_t p0 = reinterpret_cast<uintptr_t>(src) + (unsigned)iy0 * pitch + (unsigned)ix0 * 3u;
@@ -258,30 +314,71 @@ __global__ void __launch_bounds__(kWarpThreads, 3) warp_fast_kernel(
         sb[i] = __funnelshift_r(b[i], b[i + 1], f1 * 8u);
       }
       uint32_t vb[kPix], vg[kPix], vr[kPix];
-      const unsigned ay0 = nv[0] - bv;
-      blend_group_pixel<0>(st, sb, nu[0] - bu, ay0, vb[0], vg[0], vr[0]);
+      blend_group_pixel<0>(st, sb, nu[0] - bu, nv[0] - bv, vb[0], vg[0], vr[0]);
       blend_group_pixel<1>(st, sb, nu[1] - bu - 32u, nv[1] - bv, vb[1], vg[1], vr[1]);
       blend_group_pixel<2>(st, sb, nu[2] - bu - 64u, nv[2] - bv, vb[2], vg[2], vr[2]);
       blend_group_pixel<3>(st, sb, nu[3] - bu - 96u, nv[3] - bv, vb[3], vg[3], vr[3]);
-      uint8_t* d = dstf + ((size_t)py * W + px0) * 3;
       if (word_store) {
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
         __stcs(d32 + 0, __byte_perm(__byte_perm(vb[0], vg[0], 0x0040), __byte_perm(vr[0], vb[1], 0x0040), 0x5410));
         __stcs(d32 + 1, __byte_perm(__byte_perm(vg[1], vr[1], 0x0040), __byte_perm(vb[2], vg[2], 0x0040), 0x5410));
         __stcs(d32 + 2, __byte_perm(__byte_perm(vr[2], vb[3], 0x0040), __byte_perm(vg[3], vr[3], 0x0040), 0x5410));
       } else {
 #pragma unroll
-        for (int j = 0; j < kPix; ++j) { d[3 * j] = (uint8_t)vb[j]; d[3 * j + 1] = (uint8_t)vg[j]; d[3 * j + 2] = (uint8_t)vr[j]; }
+        for (int j = 0; j < kPix; ++j) { drow[3 * j] = (uint8_t)vb[j]; drow[3 * j + 1] = (uint8_t)vg[j]; drow[3 * j + 2] = (uint8_t)vr[j]; }
       }
     }
   }
-  // ---- everything the fast path declined, all lanes busy ----
-  __syncthreads();
-  const int n = qn;
-  for (int i = tid; i < n; i += kWarpThreads) {
-    const uint32_t q = queue[i];
-    slow_pixel((int)(q & 0xffffu), (int)(q >> 16), f, src, dstf, fcells, tile_count, tile_list, rowseg, segcap, crop_out,
-               W, H, ncell, tiles_x, tiles_y, border);
+  // ---- what the fast path declined, handled by this warp right away (its source rows are still in L1 / L2):
+  //      one scan for both masks (counts packed as 16-bit halves), entries in the warp's shared-memory list ----
+  const int mine = __popc(medmask) | (__popc(exmask) << 16);
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int totals = __shfl_sync(0xffffffffu, incl, 31);
+  if (totals == 0) return;
+  const int n_med = totals & 0xffff;
+  int n_ex = totals >> 16;
+  uint16_t* wq = warp_queue[warp];                          // [0, n_med): per-pixel tap fetch; then the float64 pixels
+  {
+    int slot = (incl & 0xffff) - (mine & 0xffff);
+    while (medmask != 0u) {
+      const int b = __ffs(medmask) - 1;
+      medmask &= medmask - 1u;
+      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((b >> 2) << 7));
+    }
+    slot = n_med + (incl >> 16) - (mine >> 16);
+    while (exmask != 0u) {
+      const int b = __ffs(exmask) - 1;
+      exmask &= exmask - 1u;
+      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((b >> 2) << 7));
+    }
+  }
+  __syncwarp();
+  const CellFast* ffast2 = fast + (size_t)f * ncell;
+  for (int i0 = 0; i0 < n_med; i0 += 32) {
+    const int i = i0 + lane;
+    bool failed = false;
+    unsigned e = 0u;
+    if (i < n_med) {
+      e = wq[i];
+      const int qx = tx * kTileW + (int)(e & 127u), qy = y_first + (int)(e >> 7);
+      const uint32_t* rsq = rowseg + (((size_t)f * H + qy) * tiles_x + tx) * segcap;
+      failed = !medium_pixel(qx, qy, pixel_owner(rsq, segcap, qx), src, dstf, ffast2, W, H, border);
+    }
+    const unsigned fb = __ballot_sync(0xffffffffu, failed);  // rare: the pixel is in the rounding band after all
+    if (failed) wq[n_med + n_ex + __popc(fb & ((1u << lane) - 1u))] = (uint16_t)e;
+    n_ex += __popc(fb);
+  }
+  __syncwarp();
+  const Cell* fcells = cells + (size_t)f * ncell;
+  for (int i = lane; i < n_ex; i += 32) {
+    const unsigned e = wq[n_med + i];
+    slow_pixel(tx * kTileW + (int)(e & 127u), y_first + (int)(e >> 7), f, src, dstf, fcells, tile_count, tile_list, rowseg,
+               segcap, crop_out, W, H, ncell, tiles_x, tiles_y, border);
   }
 }
 

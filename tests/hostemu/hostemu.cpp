@@ -254,7 +254,7 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
           const unsigned bad = mf::fast_group_coords(cf.a[0], cf.a[1], cf.a[2], cf.a[3], cf.a[4], cf.a[5], cf.a[6], cf.a[7],
                                                      cf.a[8], cf.thr_u, cf.thr_v, cf.bx0, cf.by0, px0, py, nu, nv);
           stats[2] += __builtin_popcount(bad);
-          push = mf::fast_group_plan(nu, nv, bad, cf.base_x, cf.base_y, cf.flags, W, H, bounds_only != 0, ix0, iy0, fg);
+          bool edge; push = mf::fast_group_plan(nu, nv, bad, cf.base_x, cf.base_y, cf.flags, W, H, bounds_only != 0, ix0, iy0, fg, edge);
         }
       }
       if (push == 15u || (npx < 4 && push)) stats[5]++;
