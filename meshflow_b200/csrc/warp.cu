@@ -35,8 +35,11 @@ static constexpr int kTileCap = 48;      // candidate cells per tile before the 
 static constexpr int kCountMask = 0xffff; // tile_count: low 16 bits = candidates, bit 16 = has a border cell
 static constexpr int kEdgeFlag = 0x10000;
 static constexpr int kWarpThreads = 256; // 32 lanes x 8 rows
-static constexpr int kFastRows = 5;      // fast path: rows per warp
-static constexpr int kFastTileH = 8 * kFastRows;   // 40: divides 720, 1080, 1440, 2160, 4320
+#ifndef MF_FAST_ROWS
+#define MF_FAST_ROWS 15
+#endif
+static constexpr int kFastRows = MF_FAST_ROWS;     // fast path: rows per warp (<= 16: one 64-bit mask of 4 bits per row)
+static constexpr int kFastTileH = 8 * kFastRows;   // 120: divides 720, 1080, 1440, 2160, 4320
 
 __global__ void __launch_bounds__(128) cell_setup_kernel(
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
@@ -457,6 +460,104 @@ __global__ void __launch_bounds__(128) crop_resize_kernel(
   }
 }
 
+// cv2.resize with the horizontal pass shared between output rows.  The crop is stretched (scale <= 1),
+// so consecutive output rows read the same source row most of the time: a thread owns 4 adjacent output
+// columns over kResizeRows rows and keeps the horizontal sums (a0*p0 + a1*p1) >> 4 of the two source
+// rows it last used -- 12 values each -- recomputing a row only when the row index changes (a
+// warp-uniform decision).  Column taps, byte phases and weights are fixed per thread, outside the row
+// loop.  Vertical pass: ((b0*s0) >> 16) + ((b1*s1) >> 16) as two high multiplies by b << 16.
+// Threads whose columns are clamped at the crop border (c1 != c0 + 1), partial groups and unaligned
+// frames take the general per-pixel form.
+#ifndef MF_RESIZE_ROWS
+#define MF_RESIZE_ROWS 16
+#endif
+static constexpr int kResizeRows = MF_RESIZE_ROWS;
+
+struct RowSums { uint32_t v[kPix][3]; };
+
+__device__ __forceinline__ void resize_hsum(const uint8_t* __restrict__ row, const unsigned (&woff)[kPix],
+                                            const unsigned (&shift)[kPix], const uint32_t (&wx)[kPix], RowSums& out) {
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row + woff[j]);
+    const uint32_t t0 = __ldg(w), t1 = __ldg(w + 1), t2 = shift[j] == 24u ? __ldg(w + 2) : 0u;
+    const uint32_t u0 = __funnelshift_r(t0, t1, shift[j]), u1 = __funnelshift_r(t1, t2, shift[j]);   // B0 G0 R0 B1 | G1 R1 . .
+    const uint32_t bg = __byte_perm(u0, u1, 0x4130), rr = __byte_perm(u0, u1, 0x0052);
+    out.v[j][0] = __dp2a_lo(wx[j], bg, 0u) >> 4;
+    out.v[j][1] = __dp2a_hi(wx[j], bg, 0u) >> 4;
+    out.v[j][2] = __dp2a_lo(wx[j], rr, 0u) >> 4;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpThreads) crop_resize_rows_kernel(
+    const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, int W, int H,
+    const int32_t* __restrict__ enc4, const int4* __restrict__ xtab, const int4* __restrict__ ytab) {
+  int left, top, right_unused, bottom_unused;
+  if (!decode_crop(enc4, W, H, left, top, right_unused, bottom_unused)) return;
+  const int f = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int px0 = blockIdx.x * kTileW + lane * kPix;
+  const int y_first = (blockIdx.y * (kWarpThreads / 32) + warp) * kResizeRows;
+  if (px0 >= W || y_first >= H) return;
+  const int npx = min(kPix, W - px0);
+  const int y_end = min(H, y_first + kResizeRows);
+  const uint8_t* src = frames_in + (size_t)f * H * W * 3;
+  uint8_t* drow = frames_out + ((size_t)f * H * W + (size_t)y_first * W + px0) * 3;
+  const unsigned pitch = (unsigned)W * 3u;
+  int c0[kPix], c1[kPix], a0[kPix], a1[kPix];
+  uint32_t wx[kPix];
+  unsigned woff[kPix], shift[kPix];
+  bool regular = npx == kPix && (pitch & 3u) == 0u && (reinterpret_cast<uintptr_t>(src) & 3u) == 0u &&
+                 (reinterpret_cast<uintptr_t>(drow) & 3u) == 0u;
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    const int4 xt = __ldg(xtab + min(px0 + j, W - 1));
+    c0[j] = left + xt.x; c1[j] = left + xt.y; a0[j] = xt.z; a1[j] = xt.w;
+    wx[j] = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
+    const unsigned b = (unsigned)c0[j] * 3u;
+    woff[j] = b & ~3u; shift[j] = (b & 3u) * 8u;
+    regular = regular && c1[j] == c0[j] + 1 && c0[j] + 4 <= W - 1;     // 12-byte reads stay inside the row
+  }
+  if (regular) {
+    RowSums A, B;
+    int ra = -1, rb = -1;
+    for (int py = y_first; py < y_end; ++py, drow += pitch) {
+      const int4 yt = __ldg(ytab + py);
+      const int r0 = top + yt.x, r1 = top + yt.y;            // warp-uniform
+      if (r0 != ra) {
+        if (r0 == rb) A = B; else resize_hsum(src + (size_t)r0 * pitch, woff, shift, wx, A);
+        ra = r0;
+      }
+      if (r1 != rb) {
+        if (r1 == ra) B = A; else resize_hsum(src + (size_t)r1 * pitch, woff, shift, wx, B);
+        rb = r1;
+      }
+      const uint32_t b0s = (uint32_t)yt.z << 16, b1s = (uint32_t)yt.w << 16;
+      uint32_t v[kPix][3];
+#pragma unroll
+      for (int j = 0; j < kPix; ++j)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)   // a0 + a1 <= 2049 and b0 + b1 <= 2049 bound the result by 255: no clamp needed
+          v[j][ch] = (__umulhi(b0s, A.v[j][ch]) + __umulhi(b1s, B.v[j][ch]) + 2u) >> 2;
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
+      __stcs(d32 + 0, __byte_perm(__byte_perm(v[0][0], v[0][1], 0x0040), __byte_perm(v[0][2], v[1][0], 0x0040), 0x5410));
+      __stcs(d32 + 1, __byte_perm(__byte_perm(v[1][1], v[1][2], 0x0040), __byte_perm(v[2][0], v[2][1], 0x0040), 0x5410));
+      __stcs(d32 + 2, __byte_perm(__byte_perm(v[2][2], v[3][0], 0x0040), __byte_perm(v[3][1], v[3][2], 0x0040), 0x5410));
+    }
+    return;
+  }
+  for (int py = y_first; py < y_end; ++py, drow += pitch) {   // general form, pixel by pixel
+    const int4 yt = __ldg(ytab + py);
+    const uint8_t* r0 = src + (size_t)(top + yt.x) * pitch;
+    const uint8_t* r1 = src + (size_t)(top + yt.y) * pitch;
+    for (int j = 0; j < npx; ++j)
+      for (int ch = 0; ch < 3; ++ch)
+        drow[3 * j + ch] = (uint8_t)resize_blend(__ldg(r0 + c0[j] * 3 + ch), __ldg(r0 + c1[j] * 3 + ch),
+                                                 __ldg(r1 + c0[j] * 3 + ch), __ldg(r1 + c1[j] * 3 + ch), a0[j], a1[j],
+                                                 yt.z, yt.w);
+  }
+}
+
 struct WarpWorkspace {
   Cell* cells;
   int* tile_count;
@@ -609,10 +710,18 @@ static int launch_crop_resize(const uint8_t* frames_in, int nf, int W, int H, co
   int4* ytab = (int4*)((char*)workspace + 256 + mf::align_up((size_t)W * sizeof(int4), 256));
   mf::resize_table_kernel<<<(W + H + 127) / 128, 128, 0, st>>>(W, H, enc4, xtab, ytab);
   if (int e = mf::check_launch("resize_table")) return e;
-  const dim3 grid((unsigned)((W + mf::kTileW - 1) / mf::kTileW), (unsigned)((H + mf::kTileH - 1) / mf::kTileH),
+  static const bool generic = [] { const char* e = getenv("MF_RESIZE_GENERIC"); return e && e[0] == '1'; }();
+  if (generic) {
+    const dim3 grid((unsigned)((W + mf::kTileW - 1) / mf::kTileW), (unsigned)((H + mf::kTileH - 1) / mf::kTileH),
+                    (unsigned)nf);
+    mf::crop_resize_kernel<<<grid, 128, 0, st>>>(frames_in, frames_out, W, H, enc4, xtab, ytab);
+    return mf::check_launch("crop_resize");
+  }
+  const int rows_per_cta = (mf::kWarpThreads / 32) * mf::kResizeRows;
+  const dim3 grid((unsigned)((W + mf::kTileW - 1) / mf::kTileW), (unsigned)((H + rows_per_cta - 1) / rows_per_cta),
                   (unsigned)nf);
-  mf::crop_resize_kernel<<<grid, 128, 0, st>>>(frames_in, frames_out, W, H, enc4, xtab, ytab);
-  return mf::check_launch("crop_resize");
+  mf::crop_resize_rows_kernel<<<grid, mf::kWarpThreads, 0, st>>>(frames_in, frames_out, W, H, enc4, xtab, ytab);
+  return mf::check_launch("crop_resize_rows");
 }
 
 extern "C" int mf_crop_combine(const int32_t* per_frame_crop, int nf, int32_t* crop_enc_out, void* stream) {

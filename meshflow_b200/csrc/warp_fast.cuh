@@ -9,7 +9,7 @@
 //                         candidate cell on that row (span_of_row: four half-planes + the exact test
 //                         for a pixel within rounding noise of a boundary), resolved by "the last cell
 //                         written wins" into <= 16 sorted segments (first x, cell id).
-//   warp_fast_kernel    : CTA = 128 x 40 output pixels, warp = 128 x 5, four adjacent pixels per thread
+//   warp_fast_kernel    : CTA = 128 x 120 output pixels, warp = 128 x 15, four adjacent pixels per thread
 //                         and row.  Per row a thread looks its cell up in the segment list, evaluates
 //                         the cell's remap coordinates in float32 in box-local form (error < eps, see
 //                         mf_math.cuh) and keeps rint() only when the value is outside the rounding
@@ -202,8 +202,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
     const CellFast* __restrict__ fast, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
     const uint32_t* __restrict__ rowseg, int segcap, int32_t* __restrict__ crop_out, int W, int H, int ncell,
     int tiles_x, int tiles_y, uint32_t border) {
-  // every pixel of a warp fits, twice (a pixel whose per-pixel tap fetch fails is listed again for the float64 path)
-  __shared__ uint16_t warp_queue[kWarpThreads / 32][2 * kTileW * kFastRows];
+  __shared__ uint16_t warp_queue[kWarpThreads / 32][kTileW * kFastRows];   // every pixel of a warp fits
   const int f = blockIdx.z, tx = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int px0 = tx * kTileW + lane * kPix;
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   int cbx0 = 0, cby0 = 0, base_x = 0, base_y = 0;
   unsigned flags = 0;
   // bit 4*r + j: pixel j of row r takes the float64 path (global queue) / the per-pixel tap fetch (this warp, below)
-  unsigned exmask = 0u, medmask = 0u;
+  unsigned long long exmask = 0ull, medmask = 0ull;
 
   // the next row's first four segments are requested one row ahead (they come from L2)
   uint4 e_next = make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
@@ -293,8 +292,8 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
         if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }   // only the group shape failed
       }
     }
-    exmask |= push << (4 * r);
-    medmask |= med << (4 * r);
+    exmask |= (unsigned long long)push << (4 * r);
+    medmask |= (unsigned long long)med << (4 * r);
     if (!kBoundsOnly && fast_group) {
       const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
       const uintptr_t p0 = reinterpret_cast<uintptr_t>(src) + (unsigned)iy0 * pitch + (unsigned)ix0 * 3u;
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   }
   // ---- what the fast path declined, handled by this warp right away (its source rows are still in L1 / L2):
   //      one scan for both masks (counts packed as 16-bit halves), entries in the warp's shared-memory list ----
-  const int mine = __popc(medmask) | (__popc(exmask) << 16);
+  const int mine = __popcll(medmask) | (__popcll(exmask) << 16);
   int incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -340,25 +339,25 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   }
   const int totals = __shfl_sync(0xffffffffu, incl, 31);
   if (totals == 0) return;
-  const int n_med = totals & 0xffff;
-  int n_ex = totals >> 16;
-  uint16_t* wq = warp_queue[warp];                          // [0, n_med): per-pixel tap fetch; then the float64 pixels
+  const int n_med = totals & 0xffff, n_ex = totals >> 16;
+  uint16_t* wq = warp_queue[warp];                          // [0, n_med): per-pixel tap fetch; [n_med, n_med + n_ex): float64
   {
     int slot = (incl & 0xffff) - (mine & 0xffff);
-    while (medmask != 0u) {
-      const int b = __ffs(medmask) - 1;
-      medmask &= medmask - 1u;
+    while (medmask != 0ull) {
+      const int b = __ffsll((long long)medmask) - 1;
+      medmask &= medmask - 1ull;
       wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((b >> 2) << 7));
     }
     slot = n_med + (incl >> 16) - (mine >> 16);
-    while (exmask != 0u) {
-      const int b = __ffs(exmask) - 1;
-      exmask &= exmask - 1u;
+    while (exmask != 0ull) {
+      const int b = __ffsll((long long)exmask) - 1;
+      exmask &= exmask - 1ull;
       wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((b >> 2) << 7));
     }
   }
   __syncwarp();
   const CellFast* ffast2 = fast + (size_t)f * ncell;
+  int n_failed = 0;                                          // pixels whose tap fetch declined, compacted to the list's front
   for (int i0 = 0; i0 < n_med; i0 += 32) {
     const int i = i0 + lane;
     bool failed = false;
@@ -370,13 +369,14 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
       failed = !medium_pixel(qx, qy, pixel_owner(rsq, segcap, qx), src, dstf, ffast2, W, H, border);
     }
     const unsigned fb = __ballot_sync(0xffffffffu, failed);  // rare: the pixel is in the rounding band after all
-    if (failed) wq[n_med + n_ex + __popc(fb & ((1u << lane) - 1u))] = (uint16_t)e;
-    n_ex += __popc(fb);
+    __syncwarp();                                            // every lane has read its entry: the front may be reused
+    if (failed) wq[n_failed + __popc(fb & ((1u << lane) - 1u))] = (uint16_t)e;
+    n_failed += __popc(fb);
   }
   __syncwarp();
   const Cell* fcells = cells + (size_t)f * ncell;
-  for (int i = lane; i < n_ex; i += 32) {
-    const unsigned e = wq[n_med + i];
+  for (int i = lane; i < n_failed + n_ex; i += 32) {
+    const unsigned e = wq[i < n_failed ? i : n_med + (i - n_failed)];
     slow_pixel(tx * kTileW + (int)(e & 127u), y_first + (int)(e >> 7), f, src, dstf, fcells, tile_count, tile_list, rowseg,
                segcap, crop_out, W, H, ncell, tiles_x, tiles_y, border);
   }

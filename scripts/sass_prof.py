@@ -15,12 +15,12 @@ hdr = sec['hdr']; data = sec['rows']
 iA = hdr.index('Source'); iE = hdr.index('Instructions Executed'); iT = hdr.index('Thread Instructions Executed'); iS = hdr.index('# Samples')
 tot = sum(int(r[iE]) for r in data)
 print(sec['name'][:70]); print('warp instr', tot, 'thread instr/px', sum(int(r[iT]) for r in data) / px, 'lanes/px', tot * 32 / px)
+with open('/tmp/sass_prof.txt', 'w') as fo:
+    for i, r in enumerate(data):
+        e = int(r[iE]); fo.write(f'{i:5d} {e*32/px:6.3f} {int(r[iT])/max(e,1):5.1f} {int(r[iS]):6d}  {r[iA]}\n')
 h = collections.Counter(); hs = collections.Counter()
 for r in data:
     t = r[iA].split(); op = (t[1] if t[0].startswith('@') else t[0]).split('.')[0]
     h[op] += int(r[iE]); hs[op] += int(r[iS])
 ts = sum(hs.values())
 for op, n in h.most_common(24): print(f'{op:10s} {n*32/px:7.2f} lanes/px  {100*n/tot:5.1f}%  samples {100*hs[op]/ts:5.1f}%')
-with open('/tmp/sass_prof.txt', 'w') as fo:
-    for i, r in enumerate(data):
-        e = int(r[iE]); fo.write(f'{i:5d} {e*32/px:6.3f} {int(r[iT])/max(e,1):5.1f} {int(r[iS]):6d}  {r[iA]}\n')
