@@ -332,6 +332,12 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     warp_bytes = 6.0 * H * W * F                       # read source once + write stabilized once, per launch
     achieved = warp_bytes / (stage_ms["warp"] / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "warp_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_1080p_frame"] * F * (W * H) / (1920.0 * 1080.0)
+        traffic_src = tj["source"]
     resize_gbs = warp_bytes / (stage_ms["crop_resize"] / 1e3) / 1e9
     out = {
         "metric": "stabilized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -344,14 +350,17 @@ def run_b200(args):
                    "crop": list(crop), "parallelism": f"frames x{world}, Jacobi vertices x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": 14 * args.steps,
+        # kernels of this library per step: feature_prepare_masks, pair_sort, row_select, median3x3, prefix,
+        # jacobi_coeff, jacobi_solve, cell_setup, tile_sort, row_segments, warp_fast, crop_combine, resize_table,
+        # crop_resize_rows, stability
+        "gpu_launches": 15 * args.steps,
         "stages_ms": stage_ms,
-        "roofline": {"kernel": "warp_kernel (mf_warp_frames, incl. cell_setup)", "bound": "hbm",
+        "roofline": {"kernel": "warp_fast_kernel (timed: the whole mf_warp_frames stage = cell_setup + tile_sort + "
+                               "row_segments + warp_fast)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read+write of this kernel from profiles/r01b_summary.md (ncu --set full,
-                     # 60 frames of 1080p: 387.6 MB + 338.3 MB), scaled to this launch's frame count
-                     "traffic": (387.63e6 + 338.31e6) / 60.0 * F * (W * H) / (1920.0 * 1080.0),
-                     "traffic_source": "profiles/r01b_summary.md", "peak_source": peak_src,
+                     # dram__bytes_read + dram__bytes_write of the stage's kernels from one ncu --set full capture
+                     # (profiles/warp_traffic.json names it), per 1080p frame, scaled to this launch
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": warp_bytes},
         "crop_resize_gbs": resize_gbs,
         "clocks": clocks,

@@ -572,6 +572,7 @@ struct alignas(16) CellFast {
 
 struct alignas(16) CellSpan {
   double al[4], be[4], ga[4];   // half-planes, already multiplied by the sign of the denominator
+  double ial[4], mrg[4];        // -1/al and the width (pixels) of the uncertain zone around the crossing; ial = 0: degenerate
   double noise;                 // |evaluated half-plane - truth| bound
   int regular;                  // 1: spans are valid; 0: resolve this cell pixel by pixel
   int pad_;
@@ -590,7 +591,7 @@ MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, in
   cf.base_x = cf.base_y = 0;
   cf.flags = (L <= 2 ? kEdgeLeft : 0u) | (Rr >= W - 3 ? kEdgeRight : 0u) | (T <= 2 ? kEdgeTop : 0u) |
              (B >= H - 3 ? kEdgeBottom : 0u);
-  for (int i = 0; i < 4; ++i) { sp.al[i] = sp.be[i] = sp.ga[i] = 0.0; }
+  for (int i = 0; i < 4; ++i) { sp.al[i] = sp.be[i] = sp.ga[i] = sp.ial[i] = sp.mrg[i] = 0.0; }
   sp.noise = 0.0; sp.regular = 0; sp.pad_ = 0;
   if (!c.bounded || c.bx0 > c.bx1) return;
   const double fx0 = (double)c.bx0, fx1 = (double)c.bx1, fy0 = (double)c.by0, fy1 = (double)c.by1;
@@ -624,6 +625,10 @@ MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, in
       const double u48 = 3.5527136788005009e-15;          // 2^-48: 32x the rounding unit times the ~6 roundings involved
       const double ref = u48 * (32.0 * magN / dmin + kmax * (magD / dmin + 1.0));   // reference X, Y vs truth (1/32-px units)
       sp.noise = 2.0 * (ref * dmax + u48 * (32.0 * magN + kmax * magD));
+      for (int i = 0; i < 4; ++i) {
+        const double aal = fabs(sp.al[i]);
+        if (aal >= 4.0 * sp.noise) { sp.ial[i] = -1.0 / sp.al[i]; sp.mrg[i] = sp.noise / aal + 1e-7; }   // mrg < 0.26
+      }
       sp.regular = 1;
     }
   }
@@ -681,18 +686,18 @@ MF_HD int span_of_row(const Cell& c, const CellSpan& sp, int y, int xlo, int xhi
   for (int i = 0; i < 4; ++i) {
     const double al = sp.al[i];
     const double rowc = sp.be[i] * yd + sp.ga[i];
-    const double aal = fabs(al);
-    if (aal < 4.0 * sp.noise) {
+    if (sp.ial[i] == 0.0) {
       // (almost) no dependence on x over any frame width the library accepts: decide the row as a whole
       const double c0 = al * (double)xlo + rowc, c1 = al * (double)xhi + rowc;
       const double cmin = c0 < c1 ? c0 : c1, cmax = c0 < c1 ? c1 : c0;
-      const double slack = sp.noise + aal;
-      if (cmin > slack) continue;
-      if (cmax < -slack) return 1;
+      if (cmin > sp.noise) continue;
+      if (cmax < -sp.noise) return 1;
       return 2;
     }
-    const double t = -rowc / al;
-    const double m = sp.noise / aal + 1e-7;               // < 0.26
+    // crossing of the half-plane with the row; the product differs from the quotient -rowc/al by an ulp,
+    // far inside the margin
+    const double t = rowc * sp.ial[i];
+    const double m = sp.mrg[i];
     if (!(t == t) || fabs(t) > 1e15) return 2;
     if (al > 0.0) {                                        // pixels x >= t
       double first = floor(t + m) + 1.0;                   // smallest integer certainly on the member side

@@ -489,7 +489,10 @@ __device__ __forceinline__ void resize_hsum(const uint8_t* __restrict__ row, con
   }
 }
 
-__global__ void __launch_bounds__(kWarpThreads) crop_resize_rows_kernel(
+#ifndef MF_RESIZE_MINBLOCKS
+#define MF_RESIZE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kWarpThreads, MF_RESIZE_MINBLOCKS) crop_resize_rows_kernel(
     const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, int W, int H,
     const int32_t* __restrict__ enc4, const int4* __restrict__ xtab, const int4* __restrict__ ytab) {
   int left, top, right_unused, bottom_unused;

@@ -219,12 +219,9 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   const uint32_t* rs = rowseg + (((size_t)f * H + y_first) * tiles_x + tx) * segcap;
   uint8_t* drow = kBoundsOnly ? nullptr : dstf + ((size_t)y_first * W + px0) * 3;
 
-  unsigned cur_id = 0xffffffffu;
-  float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, thr = -1.0f, thr_v = -1.0f;
-  int cbx0 = 0, cby0 = 0, base_x = 0, base_y = 0;
-  unsigned flags = 0;
-  // bit 4*r + j: pixel j of row r takes the float64 path (global queue) / the per-pixel tap fetch (this warp, below)
+  // four bits per row, newest row in the low bits: pixel j of the row takes the float64 path / the per-pixel tap fetch
   unsigned long long exmask = 0ull, medmask = 0ull;
+  int rows_done = 0;
 
   // the next row's first four segments are requested one row ahead (they come from L2)
   uint4 e_next = make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
@@ -233,6 +230,8 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   for (int r = 0; r < kFastRows; ++r, rs += seg_stride, drow += pitch) {
     const int py = y_first + r;
     if (py >= H) break;
+    ++rows_done;
+    exmask <<= 4; medmask <<= 4;
     if (npx <= 0) continue;
     uint4 e = e_next;
     if (r + 1 < kFastRows && py + 1 < H) e_next = __ldg(reinterpret_cast<const uint4*>(rs + seg_stride));
@@ -263,7 +262,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
     unsigned push = 0u, med = 0u;                            // bit j: pixel j -> float64 path / per-pixel tap fetch
     bool fast_group = false;
     unsigned nu[kPix], nv[kPix];
-    int ix0 = 0, iy0 = 0;
+    int ix0 = 0, iy0 = 0, base_x = 0, base_y = 0;
     if (id == kSegIrregular) {
       push = (1u << npx) - 1u;
     } else if (strad || npx < kPix) {
@@ -274,15 +273,15 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
         store_bgr4(drow, o, kPix, word_store);
       }
     } else {
-      if (id != cur_id) {
-        const float4* cp = reinterpret_cast<const float4*>(ffast + id);
-        const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
-        const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
-        a0 = q0.x; a1 = q0.y; a2 = q0.z; a3 = q0.w; a4 = q1.x; a5 = q1.y; a6 = q1.z; a7 = q1.w; a8 = q2.x; thr = q2.y;
-        cbx0 = __float_as_int(q2.z); cby0 = __float_as_int(q2.w);
-        base_x = q3.x; base_y = q3.y; flags = (unsigned)q3.z; thr_v = __int_as_float(q3.w);
-        cur_id = id;
-      }
+      // the cell's parameters come from L1 every row: cheaper than keeping 16 registers alive across the gather
+      const float4* cp = reinterpret_cast<const float4*>(ffast + id);
+      const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
+      const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
+      const float a0 = q0.x, a1 = q0.y, a2 = q0.z, a3 = q0.w, a4 = q1.x, a5 = q1.y, a6 = q1.z, a7 = q1.w, a8 = q2.x, thr = q2.y;
+      const int cbx0 = __float_as_int(q2.z), cby0 = __float_as_int(q2.w);
+      base_x = q3.x; base_y = q3.y;
+      const unsigned flags = (unsigned)q3.z;
+      const float thr_v = __int_as_float(q3.w);
       if (thr < 0.0f) {
         push = 15u;
       } else {
@@ -292,8 +291,8 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
         if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }   // only the group shape failed
       }
     }
-    exmask |= (unsigned long long)push << (4 * r);
-    medmask |= (unsigned long long)med << (4 * r);
+    exmask |= push;
+    medmask |= med;
     if (!kBoundsOnly && fast_group) {
       const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
       const uintptr_t p0 = reinterpret_cast<uintptr_t>(src) + (unsigned)iy0 * pitch + (unsigned)ix0 * 3u;
@@ -346,13 +345,13 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
     while (medmask != 0ull) {
       const int b = __ffsll((long long)medmask) - 1;
       medmask &= medmask - 1ull;
-      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((b >> 2) << 7));
+      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((rows_done - 1 - (b >> 2)) << 7));
     }
     slot = n_med + (incl >> 16) - (mine >> 16);
     while (exmask != 0ull) {
       const int b = __ffsll((long long)exmask) - 1;
       exmask &= exmask - 1ull;
-      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((b >> 2) << 7));
+      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((rows_done - 1 - (b >> 2)) << 7));
     }
   }
   __syncwarp();
