@@ -351,9 +351,9 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         # kernels of this library per step: feature_prepare_masks, pair_sort, row_select, median3x3, prefix,
-        # jacobi_coeff, jacobi_solve, cell_setup, tile_sort, row_segments, warp_fast, crop_combine, resize_table,
-        # crop_resize_rows, stability
-        "gpu_launches": 15 * args.steps,
+        # jacobi_coeff, jacobi_solve, cell_setup, tile_sort, cell_spans, row_segments, warp_fast, crop_combine,
+        # resize_table, crop_resize_rows, stability
+        "gpu_launches": 16 * args.steps,
         "stages_ms": stage_ms,
         "roofline": {"kernel": "warp_fast_kernel (timed: the whole mf_warp_frames stage = cell_setup + tile_sort + "
                                "row_segments + warp_fast)", "bound": "hbm",

@@ -581,6 +581,7 @@ struct alignas(16) CellSpan {
 static constexpr unsigned kEdgeLeft = 1u, kEdgeRight = 2u, kEdgeTop = 4u, kEdgeBottom = 8u;
 static constexpr unsigned kSegNone = 0xffffu;    // no cell covers the segment: default map, border colour
 static constexpr unsigned kSegIrregular = 0xfffeu;  // resolve every pixel of this row segment exactly
+static constexpr unsigned kSegStraddle = 0xfffdu;   // lane-owner table only: a segment starts inside the group of four
 static constexpr unsigned kSegSentinel = 0xffffffffu;
 static constexpr int kSegMax = 16;
 

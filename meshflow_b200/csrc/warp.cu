@@ -568,8 +568,15 @@ struct WarpWorkspace {
   CellFast* fast;        // fast path (warp_fast.cuh)
   CellSpan* spans;
   uint32_t* rowseg;
+  uint4* lane_owner;     // [nf][H][tiles_x] x 32 uint16: owner of each lane's group of four pixels
+  uint32_t* span_tab;    // [nf][R*C][span_rows]: member interval of a cell on each row of its box
+  int span_rows;
   int segcap;
 };
+
+// Rows of the span table per cell: twice the rest height plus slack covers any sane box; taller boxes are
+// resolved pixel by pixel.
+static int span_rows_for(int H, int R) { const int h = (H + R - 1) / R; const int s = 2 * h + 32; return s < H ? s : H; }
 
 // Segments per 128-px tile row: wide cells (16 x 16 mesh at >= 720p) need few; 16 covers 64 x 64 meshes at 720p.
 static int seg_capacity(int W, int C) { return (W / C >= 48) ? 8 : kSegMax; }
@@ -584,6 +591,9 @@ static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorks
   w.spans = cv.take<CellSpan>((size_t)nf * R * C);
   w.segcap = seg_capacity(W, C);
   w.rowseg = cv.take<uint32_t>((size_t)nf * H * tiles_x * w.segcap);
+  w.lane_owner = cv.take<uint4>((size_t)nf * H * tiles_x * 4);
+  w.span_rows = span_rows_for(H, R);
+  w.span_tab = cv.take<uint32_t>((size_t)nf * R * C * w.span_rows);
   return cv.ok();
 }
 
@@ -595,7 +605,7 @@ static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorks
 // 5-word row reads; MF_WARP_GENERIC=1 forces the generic kernel (A/B comparisons).
 static bool use_fast_path(int W, int H, int R, int C) {
   static const bool forced_generic = [] { const char* e = getenv("MF_WARP_GENERIC"); return e && e[0] == '1'; }();
-  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && (int64_t)R * C < (int64_t)mf::kSegIrregular;
+  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && (int64_t)R * C < (int64_t)mf::kSegStraddle;
 }
 
 extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {
@@ -621,9 +631,13 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
   mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
   if (int e = mf::check_launch("tile_sort")) return e;
   if (fast) {
+    const int64_t nspan = ncells * w.span_rows;
+    mf::cell_spans_kernel<<<(unsigned)((nspan + 127) / 128), 128, 0, st>>>(w.cells, w.spans, ncells, w.span_rows, w.span_tab);
+    if (int e = mf::check_launch("cell_spans")) return e;
     const int64_t nrows = (int64_t)nf * H * tiles_x;
     mf::row_segments_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
-        w.cells, w.spans, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.segcap, w.rowseg);
+        w.cells, w.span_tab, w.span_rows, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.segcap, w.rowseg,
+        w.lane_owner);
     return mf::check_launch("row_segments");
   }
   return MF_OK;
@@ -650,8 +664,8 @@ extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
   if (fast) {
     mf::warp_fast_kernel<true><<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(
-        nullptr, nullptr, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, w.segcap, crop_out, W, H, R * C, tiles_x,
-        tiles_y, 0u);
+        nullptr, nullptr, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, (const uint16_t*)w.lane_owner, w.segcap,
+        crop_out, W, H, R * C, tiles_x, tiles_y, 0u);
     return mf::check_launch("warp_fast_bounds");
   }
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
@@ -686,8 +700,8 @@ extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const d
   if (fast) {
     const uint32_t border = (uint32_t)(border_b & 255) | ((uint32_t)(border_g & 255) << 8) | ((uint32_t)(border_r & 255) << 16);
     mf::warp_fast_kernel<false><<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(
-        frames_in, frames_out, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, w.segcap, crop_out, W, H, R * C,
-        tiles_x, tiles_y, border);
+        frames_in, frames_out, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, (const uint16_t*)w.lane_owner, w.segcap,
+        crop_out, W, H, R * C, tiles_x, tiles_y, border);
     return mf::check_launch("warp_fast");
   }
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);

@@ -5,10 +5,12 @@
 // 190 instructions per pixel, issue-bound at 10 % of the HBM roofline.  The fast path moves every
 // decision that does not depend on pixel data out of the pixel loop:
 //
-//   row_segments_kernel : one thread per (frame, row, 128-px tile): exact member interval of every
-//                         candidate cell on that row (span_of_row: four half-planes + the exact test
-//                         for a pixel within rounding noise of a boundary), resolved by "the last cell
-//                         written wins" into <= 16 sorted segments (first x, cell id).
+//   cell_spans_kernel   : one thread per (frame, cell, row of the cell's box): exact member interval of the
+//                         cell on that row (span_of_row: four half-planes + the exact test for a pixel
+//                         within rounding noise of a boundary).
+//   row_segments_kernel : one thread per (frame, row, 128-px tile): the candidates' intervals resolved by
+//                         "the last cell written wins" into <= 16 sorted segments (first x, cell id), and
+//                         the owner of each lane's group of four pixels (what the pixel kernel reads).
 //   warp_fast_kernel    : CTA = 128 x 120 output pixels, warp = 128 x 15, four adjacent pixels per thread
 //                         and row.  Per row a thread looks its cell up in the segment list, evaluates
 //                         the cell's remap coordinates in float32 in box-local form (error < eps, see
@@ -28,10 +30,38 @@
 
 namespace mf {
 
+// Member interval of every cell on every row of its support box: one thread per (frame, cell, row of the
+// box).  span_tab[(f * ncell + id) * span_rows + (y - by0)] = a | b << 16 (a > b: no member pixel;
+// kSpanIrregular: the row cannot be described by an interval with certainty).  Cells whose box is taller than
+// span_rows are treated as irregular by row_segments_kernel.
+static constexpr uint32_t kSpanIrregular = 0xffffffffu;
+static constexpr uint32_t kSpanEmpty = 0x00000001u;          // a = 1, b = 0
+
+__global__ void __launch_bounds__(128) cell_spans_kernel(const Cell* __restrict__ cells, const CellSpan* __restrict__ spans,
+                                                         int64_t ncells_total, int span_rows, uint32_t* __restrict__ span_tab) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ncells_total * span_rows) return;
+  const int64_t cid = idx / span_rows;
+  const int rl = (int)(idx - cid * span_rows);
+  const Cell& c = cells[cid];
+  const int4 box = __ldg(reinterpret_cast<const int4*>(&c));
+  const int y = box.y + rl;
+  if (box.x > box.z || y > box.w) return;
+  const CellSpan& sp = spans[cid];
+  uint32_t out = kSpanIrregular;
+  if (sp.regular) {
+    int a, b;
+    const int st = span_of_row(c, sp, y, box.x, box.z, a, b);
+    if (st == 0) out = (uint32_t)a | ((uint32_t)b << 16);
+    else if (st == 1) out = kSpanEmpty;
+  }
+  span_tab[idx] = out;
+}
+
 __global__ void __launch_bounds__(128) row_segments_kernel(
-    const Cell* __restrict__ cells, const CellSpan* __restrict__ spans, const int* __restrict__ tile_count,
+    const Cell* __restrict__ cells, const uint32_t* __restrict__ span_tab, int span_rows, const int* __restrict__ tile_count,
     const uint16_t* __restrict__ tile_list, int nf, int W, int H, int ncell, int tiles_x, int tiles_y, int segcap,
-    uint32_t* __restrict__ rowseg) {
+    uint32_t* __restrict__ rowseg, uint4* __restrict__ lane_owner) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)nf * H * tiles_x;
   if (idx >= total) return;
@@ -46,19 +76,17 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   sb.begin(x0, x1);
   bool irregular = nraw > kTileCap;
   const Cell* fcells = cells + (size_t)f * ncell;
-  const CellSpan* fspans = spans + (size_t)f * ncell;
+  const uint32_t* fspan = span_tab + (size_t)f * ncell * span_rows;
   const uint16_t* list = tile_list + tile * kTileCap;       // sorted by descending id
   for (int k = 0; k < nraw && !irregular; ++k) {
     const int id = __ldg(list + k);
-    const Cell& c = fcells[id];
-    const int4 box = __ldg(reinterpret_cast<const int4*>(&c));
+    const int4 box = __ldg(reinterpret_cast<const int4*>(fcells + id));
     if (y < box.y || y > box.w || x1 < box.x || x0 > box.z) continue;
-    const CellSpan& sp = fspans[id];
-    if (!sp.regular) { irregular = true; break; }
-    int a, b;
-    const int st = span_of_row(c, sp, y, max(x0, box.x), min(x1, box.z), a, b);
-    if (st == 2) { irregular = true; break; }
-    if (st == 0) sb.cover(a, b, (unsigned)id, segcap);
+    if (y - box.y >= span_rows) { irregular = true; break; }
+    const uint32_t spn = __ldg(fspan + (size_t)id * span_rows + (y - box.y));
+    if (spn == kSpanIrregular) { irregular = true; break; }
+    const int a = max((int)(spn & 0xffffu), x0), b = min((int)(spn >> 16), x1);
+    if (a <= b) sb.cover(a, b, (unsigned)id, segcap);
     if (sb.overflow) { irregular = true; break; }
     if (sb.done()) break;
   }
@@ -69,6 +97,30 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   } else {
     for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : kSegSentinel;
   }
+  // owner of each lane's group of four pixels (what the pixel kernel reads: one 16-bit load per lane and row)
+  uint32_t packed[16];
+  if (ns < 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) packed[i] = kSegIrregular | (kSegIrregular << 16);
+  } else {
+    int si = 0;
+    unsigned cur = sb.seg[0] & 0xffffu;
+    int next_x = ns > 1 ? (int)(sb.seg[1] >> 16) : 0x7fffffff;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const int g0 = x0 + kPix * l;
+      while (next_x <= g0) {                                 // segments are sorted: si only moves forward
+        ++si;
+        cur = sb.seg[si] & 0xffffu;
+        next_x = si + 1 < ns ? (int)(sb.seg[si + 1] >> 16) : 0x7fffffff;
+      }
+      const unsigned o = next_x <= g0 + kPix - 1 ? kSegStraddle : cur;
+      if (l & 1) packed[l >> 1] |= o << 16; else packed[l >> 1] = o;
+    }
+  }
+  uint4* lo = lane_owner + (size_t)idx * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) lo[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
 }
 
 // Tap fetch + blend + 3-byte store of one pixel from its 1/32-px source coordinate.
@@ -200,8 +252,8 @@ template <bool kBoundsOnly>
 __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_kernel(
     const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, const Cell* __restrict__ cells,
     const CellFast* __restrict__ fast, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
-    const uint32_t* __restrict__ rowseg, int segcap, int32_t* __restrict__ crop_out, int W, int H, int ncell,
-    int tiles_x, int tiles_y, uint32_t border) {
+    const uint32_t* __restrict__ rowseg, const uint16_t* __restrict__ lane_owner, int segcap,
+    int32_t* __restrict__ crop_out, int W, int H, int ncell, int tiles_x, int tiles_y, uint32_t border) {
   __shared__ uint16_t warp_queue[kWarpThreads / 32][kTileW * kFastRows];   // every pixel of a warp fits
   const int f = blockIdx.z, tx = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -213,59 +265,38 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   const CellFast* ffast = fast + (size_t)f * ncell;
   const unsigned pitch = (unsigned)W * 3u;
   const bool word_store = ((pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(dstf) & 3u) == 0u);
-  const uint32_t key = ((uint32_t)px0 << 16) | 0xffffu;
   // running pointers: one add per row instead of a 64-bit multiply chain
-  const size_t seg_stride = (size_t)tiles_x * segcap;
-  const uint32_t* rs = rowseg + (((size_t)f * H + y_first) * tiles_x + tx) * segcap;
+  const size_t own_stride = (size_t)tiles_x * 32;
+  const uint16_t* own = lane_owner + (((size_t)f * H + y_first) * tiles_x + tx) * 32 + lane;
   uint8_t* drow = kBoundsOnly ? nullptr : dstf + ((size_t)y_first * W + px0) * 3;
 
   // four bits per row, newest row in the low bits: pixel j of the row takes the float64 path / the per-pixel tap fetch
   unsigned long long exmask = 0ull, medmask = 0ull;
   int rows_done = 0;
 
-  // the next row's first four segments are requested one row ahead (they come from L2)
-  uint4 e_next = make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
-  if (y_first < H && npx > 0) e_next = __ldg(reinterpret_cast<const uint4*>(rs));
+  // the owner of the next row's group is requested one row ahead (it comes from L2)
+  unsigned own_next = kSegNone;
+  if (y_first < H && npx > 0) own_next = __ldg(own);
 #pragma unroll 1
-  for (int r = 0; r < kFastRows; ++r, rs += seg_stride, drow += pitch) {
+  for (int r = 0; r < kFastRows; ++r, own += own_stride, drow += pitch) {
     const int py = y_first + r;
     if (py >= H) break;
     ++rows_done;
     exmask <<= 4; medmask <<= 4;
     if (npx <= 0) continue;
-    uint4 e = e_next;
-    if (r + 1 < kFastRows && py + 1 < H) e_next = __ldg(reinterpret_cast<const uint4*>(rs + seg_stride));
+    const unsigned id = own_next;
+    if (r + 1 < kFastRows && py + 1 < H) own_next = __ldg(own + own_stride);
     if (kBoundsOnly) {                                       // only tiles that hold a border cell can produce a hit
       const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
       if (!(__ldg(tile_count + tile) & kEdgeFlag)) continue;
     }
-    // ---- owner of the group from the row's segment list ----
-    uint32_t cur = e.x;
-    bool strad = false;
-#define MF_SEG_STEP(v) { if ((v) <= key) cur = (v); strad = strad || (((v) - key - 1u) < 0x30000u); }
-    if (e.y != kSegSentinel) {
-      MF_SEG_STEP(e.y);
-      if (e.z != kSegSentinel) {
-        MF_SEG_STEP(e.z);
-        if (e.w != kSegSentinel) {
-          MF_SEG_STEP(e.w);
-          for (int q = 4; q < segcap; q += 4) {
-            e = __ldg(reinterpret_cast<const uint4*>(rs + q));
-            if (e.x == kSegSentinel) break;
-            MF_SEG_STEP(e.x); MF_SEG_STEP(e.y); MF_SEG_STEP(e.z); MF_SEG_STEP(e.w);
-          }
-        }
-      }
-    }
-#undef MF_SEG_STEP
-    const unsigned id = cur & 0xffffu;
     unsigned push = 0u, med = 0u;                            // bit j: pixel j -> float64 path / per-pixel tap fetch
     bool fast_group = false;
     unsigned nu[kPix], nv[kPix];
     int ix0 = 0, iy0 = 0, base_x = 0, base_y = 0;
     if (id == kSegIrregular) {
       push = (1u << npx) - 1u;
-    } else if (strad || npx < kPix) {
+    } else if (id == kSegStraddle || npx < kPix) {
       med = (1u << npx) - 1u;
     } else if (id == kSegNone) {
       if (!kBoundsOnly) {                                    // no cell: map (W+1, H+1), border colour, no crop hit
