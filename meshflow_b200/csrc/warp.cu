@@ -631,7 +631,7 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
   mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
   if (int e = mf::check_launch("tile_sort")) return e;
   if (fast) {
-    const int64_t nspan = ncells * w.span_rows;
+    const int64_t nspan = ncells * ((w.span_rows + mf::kSpanRowsPerThread - 1) / mf::kSpanRowsPerThread);
     mf::cell_spans_kernel<<<(unsigned)((nspan + 127) / 128), 128, 0, st>>>(w.cells, w.spans, ncells, w.span_rows, w.span_tab);
     if (int e = mf::check_launch("cell_spans")) return e;
     const int64_t nrows = (int64_t)nf * H * tiles_x;

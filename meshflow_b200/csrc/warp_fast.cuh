@@ -37,25 +37,34 @@ namespace mf {
 static constexpr uint32_t kSpanIrregular = 0xffffffffu;
 static constexpr uint32_t kSpanEmpty = 0x00000001u;          // a = 1, b = 0
 
+static constexpr int kSpanRowsPerThread = 4;                 // independent rows per thread: four chains in flight
+
 __global__ void __launch_bounds__(128) cell_spans_kernel(const Cell* __restrict__ cells, const CellSpan* __restrict__ spans,
                                                          int64_t ncells_total, int span_rows, uint32_t* __restrict__ span_tab) {
+  const int chunks = (span_rows + kSpanRowsPerThread - 1) / kSpanRowsPerThread;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= ncells_total * span_rows) return;
-  const int64_t cid = idx / span_rows;
-  const int rl = (int)(idx - cid * span_rows);
+  if (idx >= ncells_total * chunks) return;
+  const int64_t cid = idx / chunks;
+  const int rl0 = (int)(idx - cid * chunks) * kSpanRowsPerThread;
   const Cell& c = cells[cid];
   const int4 box = __ldg(reinterpret_cast<const int4*>(&c));
-  const int y = box.y + rl;
-  if (box.x > box.z || y > box.w) return;
+  if (box.x > box.z || box.y + rl0 > box.w) return;
   const CellSpan& sp = spans[cid];
-  uint32_t out = kSpanIrregular;
-  if (sp.regular) {
-    int a, b;
-    const int st = span_of_row(c, sp, y, box.x, box.z, a, b);
-    if (st == 0) out = (uint32_t)a | ((uint32_t)b << 16);
-    else if (st == 1) out = kSpanEmpty;
+  const bool regular = sp.regular != 0;
+  uint32_t* out = span_tab + cid * span_rows;
+#pragma unroll
+  for (int k = 0; k < kSpanRowsPerThread; ++k) {
+    const int rl = rl0 + k, y = box.y + rl;
+    if (rl >= span_rows || y > box.w) break;
+    uint32_t v = kSpanIrregular;
+    if (regular) {
+      int a, b;
+      const int st = span_of_row(c, sp, y, box.x, box.z, a, b);
+      if (st == 0) v = (uint32_t)a | ((uint32_t)b << 16);
+      else if (st == 1) v = kSpanEmpty;
+    }
+    out[rl] = v;
   }
-  span_tab[idx] = out;
 }
 
 __global__ void __launch_bounds__(128) row_segments_kernel(
@@ -78,17 +87,32 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   const Cell* fcells = cells + (size_t)f * ncell;
   const uint32_t* fspan = span_tab + (size_t)f * ncell * span_rows;
   const uint16_t* list = tile_list + tile * kTileCap;       // sorted by descending id
-  for (int k = 0; k < nraw && !irregular; ++k) {
-    const int id = __ldg(list + k);
-    const int4 box = __ldg(reinterpret_cast<const int4*>(fcells + id));
-    if (y < box.y || y > box.w || x1 < box.x || x0 > box.z) continue;
-    if (y - box.y >= span_rows) { irregular = true; break; }
-    const uint32_t spn = __ldg(fspan + (size_t)id * span_rows + (y - box.y));
-    if (spn == kSpanIrregular) { irregular = true; break; }
-    const int a = max((int)(spn & 0xffffu), x0), b = min((int)(spn >> 16), x1);
-    if (a <= b) sb.cover(a, b, (unsigned)id, segcap);
-    if (sb.overflow) { irregular = true; break; }
-    if (sb.done()) break;
+  // candidates four at a time: ids, boxes and spans of a group are independent loads
+  bool done = false;
+  for (int k0 = 0; k0 < nraw && !irregular && !done; k0 += 4) {
+    int id[4];
+    int4 box[4];
+    uint32_t spn[4];
+    bool use[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) id[j] = k0 + j < nraw ? (int)__ldg(list + k0 + j) : -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) box[j] = id[j] >= 0 ? __ldg(reinterpret_cast<const int4*>(fcells + id[j])) : make_int4(1, 1, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      use[j] = !(y < box[j].y || y > box[j].w || x1 < box[j].x || x0 > box[j].z);
+      const bool tall = use[j] && y - box[j].y >= span_rows;
+      spn[j] = tall ? kSpanIrregular : (use[j] ? __ldg(fspan + (size_t)id[j] * span_rows + (y - box[j].y)) : kSpanEmpty);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!use[j] || irregular || done) continue;
+      if (spn[j] == kSpanIrregular) { irregular = true; continue; }
+      const int a = max((int)(spn[j] & 0xffffu), x0), b = min((int)(spn[j] >> 16), x1);
+      if (a <= b) sb.cover(a, b, (unsigned)id[j], segcap);
+      if (sb.overflow) { irregular = true; continue; }
+      if (sb.done()) done = true;
+    }
   }
   int ns = irregular ? -1 : sb.finish(segcap);
   if (ns < 0) {

@@ -202,6 +202,24 @@ def test_warp_fast_path_equals_generic_kernel_on_camera_like_warps(W, H, R, C):
     assert torch.equal(core.warp_crop_bounds(_dev(u, core), _dev(s, core)), crop_gen)
 
 
+def test_warp_many_frames_back_to_back_on_one_workspace():
+    """70 frames per call, three calls in a row on the same workspace (different displacements in between): same
+    frames and crop edges as the generic kernel every time."""
+    W, H, R, C, F = 320, 200, 8, 8, 70
+    rng = np.random.default_rng(77)
+    frames, u, s = synth.synthetic_warp_inputs(rng, F, W, H, R, C, per_vertex=1.0, per_frame=2.0)
+    core = _core(W, H, R, C, border_bgr=(3, 2, 1))
+    fd, ud, sd = _dev(frames, core), _dev(u, core), _dev(s, core)
+    gen, crop_gen, _ = core.warp_frames(fd, ud, sd, return_maps=True)
+    a, crop_a = core.warp_frames(fd, ud, sd)
+    b, crop_b = core.warp_frames(fd, ud, _dev(u, core))          # identity right behind it, same workspace
+    c, crop_c = core.warp_frames(fd, ud, sd)
+    assert torch.equal(a, gen) and torch.equal(crop_a, crop_gen)
+    assert torch.equal(b, fd)
+    assert torch.equal(c, gen) and torch.equal(crop_c, crop_gen)
+    assert torch.equal(core.warp_crop_bounds(ud, sd), crop_gen)
+
+
 def test_warp_identity_is_a_copy():
     rng = np.random.default_rng(0)
     frames = rng.integers(0, 256, (2, 180, 320, 3), dtype=np.uint8)
