@@ -663,7 +663,9 @@ MF_HD void cell_fast_setup(const Cell& c, int L, int Rr, int T, int B, int W, in
     const double umax = 32.0 * (double)(((Rr - L > B - T ? Rr - L : B - T) + 1) / 2 + 2);
     const double dn = dmin / fabs(d0);
     const double u24 = 5.9604644775390625e-08;             // 2^-24
-    const double eps = u24 * (4.0 * (su > sv ? su : sv) + 8.0 * umax * sd) / dn + 1e-5;
+    // |float32 value - truth| <= u*(3.01*S + U_max*(3.01*S_d + 3*d_n))/d_n + O(u^2)  (numerator and denominator: rounded
+    // coefficients + two FMAs each; rcp.approx: 1 ulp; one product), d_n <= 1 <= S_d
+    const double eps = u24 * (3.1 * (su > sv ? su : sv) + 6.2 * umax * sd) / dn + 1e-5;
     // half a float32 ulp of the absolute coordinate, in 1/32-px units: 16 * 2^(e-23) for |coordinate| < 2^(e+1)
     double tie_u = 16.0 * 1.1920928955078125e-07, tie_v = tie_u;
     const int al = L - 1 < 0 ? 1 - L : L - 1, at = T - 1 < 0 ? 1 - T : T - 1;

@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
       uint32_t t[5], b[5];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { t[i] = __ldg(w0 + i); b[i] = __ldg(w1 + i); }
+#ifndef MF_FAST_NO_PREFETCH
+      // the next output row reads this window one source row further down: its bottom row is the only new line
+      if (iy0 + 2 < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + pitch + 8u));
+#endif
       t[4] = f0 >= 2u ? __ldg(w0 + 4) : 0u;
       b[4] = f1 >= 2u ? __ldg(w1 + 4) : 0u;
       uint32_t st[4], sb[4];
