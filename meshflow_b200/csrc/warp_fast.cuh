@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   const int npx = min(kPix, W - px0);                        // <= 0: this lane has no pixels
   const uint8_t* src = frames_in + (size_t)f * H * W * 3;
   uint8_t* dstf = kBoundsOnly ? nullptr : frames_out + (size_t)f * H * W * 3;
-  const CellFast* ffast = fast + (size_t)f * ncell;
+  const unsigned fcell0 = (unsigned)f * (unsigned)ncell;     // < 2^32: at most 65535 frames x 65533 cells
   const unsigned pitch = (unsigned)W * 3u;
   const bool word_store = ((pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(dstf) & 3u) == 0u);
   // running pointers: one add per row instead of a 64-bit multiply chain
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
       }
     } else {
       // the cell's parameters come from L1 every row: cheaper than keeping 16 registers alive across the gather
-      const float4* cp = reinterpret_cast<const float4*>(ffast + id);
+      const float4* cp = reinterpret_cast<const float4*>(fast + (size_t)(fcell0 + id));
       const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
       const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
       const float a0 = q0.x, a1 = q0.y, a2 = q0.z, a3 = q0.w, a4 = q1.x, a5 = q1.y, a6 = q1.z, a7 = q1.w, a8 = q2.x, thr = q2.y;
@@ -337,14 +337,13 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
       base_x = q3.x; base_y = q3.y;
       const unsigned flags = (unsigned)q3.z;
       const float thr_v = __int_as_float(q3.w);
-      if (thr < 0.0f) {
-        push = 15u;
-      } else {
-        const unsigned bad = fast_group_coords(a0, a1, a2, a3, a4, a5, a6, a7, a8, thr, thr_v, cbx0, cby0, px0, py, nu, nv);
-        bool edge;
-        push = fast_group_plan(nu, nv, bad, base_x, base_y, flags, W, H, kBoundsOnly, ix0, iy0, fast_group, edge);
-        if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }   // only the group shape failed
-      }
+      // no early exit for cells without float32 form (thr < 0: their coefficients are zero, every pixel comes out
+      // "in the band"): a branch here would serialise the four parameter loads behind the first one
+      const unsigned bad = fast_group_coords(a0, a1, a2, a3, a4, a5, a6, a7, a8, thr, thr_v, cbx0, cby0, px0, py, nu, nv);
+      bool edge;
+      push = fast_group_plan(nu, nv, bad, base_x, base_y, flags, W, H, kBoundsOnly, ix0, iy0, fast_group, edge);
+      if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }   // only the group shape failed
+      if (thr < 0.0f) { push = 15u; med = 0u; fast_group = false; }
     }
     exmask |= push;
     medmask |= med;
