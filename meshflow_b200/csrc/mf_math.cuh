@@ -862,4 +862,23 @@ MF_HD unsigned seg_group_owner(const unsigned* seg, int cap, int px0, bool& stra
   return cur & 0xffffu;
 }
 
+
+// One pixel on its own (a pixel whose GROUP failed a shape condition): float32 coordinate of the pixel through its
+// own cell; true + the 1/32-px source coordinate (sx, sy) when the pixel is outside the rounding band and cannot
+// satisfy a crop-edge search, false when it needs the float64 sequence after all.
+MF_HD bool medium_coords(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7, float a8,
+                         float thr_u, float thr_v, int cbx0, int cby0, int base_x, int base_y, unsigned flags, int px,
+                         int py, int W, int H, int& sx, int& sy) {
+  if (!(thr_u >= 0.0f)) return false;
+  const float fy = (float)(py - cby0), fx = (float)(px - cbx0);
+  unsigned nu, nv;
+  if (!fast_coords(a0, a3, a6, fmaf(a1, fy, a2), fmaf(a4, fy, a5), fmaf(a7, fy, a8), fx, thr_u, thr_v, nu, nv)) return false;
+  sx = (int)(nu - kRoundMagicBits) + base_x;
+  sy = (int)(nv - kRoundMagicBits) + base_y;
+  if (flags != 0u && (((flags & kEdgeLeft) && sx < 32 + 2) || ((flags & kEdgeRight) && sx > 32 * (W - 2) - 2) ||
+                      ((flags & kEdgeTop) && sy < 32 + 2) || ((flags & kEdgeBottom) && sy > 32 * (H - 2) - 2)))
+    return false;
+  return true;
+}
+
 }  // namespace mf

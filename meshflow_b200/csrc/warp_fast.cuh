@@ -194,16 +194,9 @@ __device__ __forceinline__ bool medium_pixel(int px, int py, unsigned id, const 
   const float4* cp = reinterpret_cast<const float4*>(ffast + id);
   const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
   const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
-  if (!(q2.y >= 0.0f)) return false;
-  const float fy = (float)(py - __float_as_int(q2.w)), fx = (float)(px - __float_as_int(q2.z));
-  unsigned nu, nv;
-  if (!fast_coords(q0.x, q0.w, q1.z, fmaf(q0.y, fy, q0.z), fmaf(q1.x, fy, q1.y), fmaf(q1.w, fy, q2.x), fx, q2.y,
-                   __int_as_float(q3.w), nu, nv))
-    return false;
-  const int sx = (int)(nu - kRoundMagicBits) + q3.x, sy = (int)(nv - kRoundMagicBits) + q3.y;
-  const unsigned flags = (unsigned)q3.z;
-  if (flags != 0u && (((flags & kEdgeLeft) && sx < 32 + 2) || ((flags & kEdgeRight) && sx > 32 * (W - 2) - 2) ||
-                      ((flags & kEdgeTop) && sy < 32 + 2) || ((flags & kEdgeBottom) && sy > 32 * (H - 2) - 2)))
+  int sx, sy;
+  if (!medium_coords(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, __int_as_float(q3.w), __float_as_int(q2.z),
+                     __float_as_int(q2.w), q3.x, q3.y, (unsigned)q3.z, px, py, W, H, sx, sy))
     return false;
   if (dst_frame != nullptr) remap_store_pixel(src, dst_frame, px, py, W, H, sx >> 5, sy >> 5, sx & 31, sy & 31, border);
   return true;

@@ -227,7 +227,7 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
       else for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : mf::kSegSentinel;
     }
   int crop[4] = {0, 0, W - 1, H - 1};
-  std::vector<std::pair<int, int>> queue;
+  std::vector<std::pair<int, int>> queue, medium;           // float64 path / per-pixel tap fetch (kernel: medmask)
   const int bord[3] = {bb, bg, br};
   for (int py = 0; py < H; ++py)
     for (int px0 = 0; px0 < W; px0 += 4) {
@@ -243,8 +243,9 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
       const unsigned* rs = &rowseg[((size_t)py * tiles_x + tx) * segcap];
       bool strad;
       const unsigned id = mf::seg_group_owner(rs, segcap, px0, strad);
-      unsigned push = 0u; bool fg = false; unsigned nu[4], nv[4]; int ix0 = 0, iy0 = 0;
-      if (strad || id == mf::kSegIrregular || npx < 4) push = (1u << npx) - 1u;
+      unsigned push = 0u, med = 0u; bool fg = false; unsigned nu[4], nv[4]; int ix0 = 0, iy0 = 0;
+      if (id == mf::kSegIrregular) push = (1u << npx) - 1u;
+      else if (strad || npx < 4) med = (1u << npx) - 1u;
       else if (id == mf::kSegNone) {
         if (!bounds_only) for (int j = 0; j < 4; ++j) for (int ch = 0; ch < 3; ++ch) dst[((size_t)py * W + px0 + j) * 3 + ch] = (uint8_t)bord[ch];
       } else {
@@ -255,10 +256,12 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
                                                      cf.a[8], cf.thr_u, cf.thr_v, cf.bx0, cf.by0, px0, py, nu, nv);
           stats[2] += __builtin_popcount(bad);
           bool edge; push = mf::fast_group_plan(nu, nv, bad, cf.base_x, cf.base_y, cf.flags, W, H, bounds_only != 0, ix0, iy0, fg, edge);
+          if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }
         }
       }
       if (push == 15u || (npx < 4 && push)) stats[5]++;
       for (int j = 0; j < 4; ++j) if (push & (1u << j)) queue.push_back({px0 + j, py});
+      for (int j = 0; j < 4; ++j) if (med & (1u << j)) medium.push_back({px0 + j, py});
       if (fg && !bounds_only) {
         const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
         for (int j = 0; j < 4; ++j) {
@@ -271,6 +274,20 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
         stats[0] += 4;
       }
     }
+  for (auto& q : medium) {                                  // medium_pixel of the kernel
+    const int px = q.first, py = q.second, tx = px / kTileW;
+    const unsigned id = mf::seg_owner(&rowseg[((size_t)py * tiles_x + tx) * segcap], segcap, px);
+    if (id == mf::kSegIrregular) { queue.push_back(q); continue; }
+    if (id == mf::kSegNone) {
+      if (!bounds_only) for (int ch = 0; ch < 3; ++ch) dst[((size_t)py * W + px) * 3 + ch] = (uint8_t)bord[ch];
+      continue;
+    }
+    const mf::CellFast& cf = fast[id];
+    int sx, sy;
+    if (!mf::medium_coords(cf.a[0], cf.a[1], cf.a[2], cf.a[3], cf.a[4], cf.a[5], cf.a[6], cf.a[7], cf.a[8], cf.thr_u, cf.thr_v,
+                           cf.bx0, cf.by0, cf.base_x, cf.base_y, cf.flags, px, py, W, H, sx, sy)) { queue.push_back(q); continue; }
+    if (!bounds_only) mf::remap_pixel(src, W, H, sx >> 5, sy >> 5, sx & 31, sy & 31, bb, bg, br, dst + ((size_t)py * W + px) * 3);
+  }
   stats[1] = (long long)queue.size();
   for (auto& q : queue) {
     const int px = q.first, py = q.second, tx = px / kTileW;
