@@ -311,12 +311,12 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
     bool fast_group = false;
     unsigned nu[kPix], nv[kPix];
     int ix0 = 0, iy0 = 0, base_x = 0, base_y = 0;
-    if (id == kSegIrregular) {
-      push = (1u << npx) - 1u;
-    } else if (id == kSegStraddle || npx < kPix) {
-      med = (1u << npx) - 1u;
-    } else if (id == kSegNone) {
-      if (!kBoundsOnly) {                                    // no cell: map (W+1, H+1), border colour, no crop hit
+    if (id >= kSegStraddle || npx < kPix) {                  // one test on the hot path; the rare owners sort themselves out here
+      if (id == kSegIrregular) {
+        push = (1u << npx) - 1u;
+      } else if (id != kSegNone || npx < kPix) {
+        med = (1u << npx) - 1u;
+      } else if (!kBoundsOnly) {                             // no cell: map (W+1, H+1), border colour, no crop hit
         uint32_t o[kPix] = {border, border, border, border};
         store_bgr4(drow, o, kPix, word_store);
       }
