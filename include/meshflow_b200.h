@@ -103,7 +103,11 @@ int mf_jacobi_solve(const double* u, const double* homographies, double* s, int 
  *                 border b,g,r)
  *   crop_out    : [nf,4] int32 per-frame (left, top, right, bottom) (mfs.py:1075-1098); the caller
  *                 combines them with max/max/min/min (mfs.py:1103-1106; an all-reduce when sharded)
- *   map_out     : optional [nf, H, W, 2] float32 (map_x, map_y) for parity checks; may be NULL
+ *   map_out     : optional [nf, H, W, 2] float32 (map_x, map_y) for parity checks; may be NULL.  The float32
+ *                 maps only exist in the generic kernel, so asking for them selects it; without map_out the
+ *                 production path runs (row segments + float32 coordinates outside a proven rounding band,
+ *                 csrc/warp_fast.cuh) -- same frames_out and crop_out, bit for bit.  Environment switches
+ *                 for A/B runs: MF_WARP_GENERIC=1, MF_RESIZE_GENERIC=1.
  * ---------------------------------------------------------------------------------------------- */
 size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C);
 int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s, const float* vertex_xy,

@@ -42,6 +42,7 @@ static constexpr int kFastRows = MF_FAST_ROWS;     // fast path: rows per warp (
 static constexpr int kFastTileH = 8 * kFastRows;   // 120: divides 720, 1080, 1440, 2160, 4320
 
 __global__ void __launch_bounds__(128) cell_setup_kernel(
+
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
     int nf, int W, int H, int R, int C, int tiles_x, int tiles_y, Cell* __restrict__ cells,
     CellFast* __restrict__ fast, CellSpan* __restrict__ spans,

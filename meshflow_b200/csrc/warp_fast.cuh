@@ -5,19 +5,21 @@
 // 190 instructions per pixel, issue-bound at 10 % of the HBM roofline.  The fast path moves every
 // decision that does not depend on pixel data out of the pixel loop:
 //
-//   cell_spans_kernel   : one thread per (frame, cell, row of the cell's box): exact member interval of the
-//                         cell on that row (span_of_row: four half-planes + the exact test for a pixel
+//   cell_spans_kernel   : one thread per (frame, cell, four rows of the cell's box): exact member interval of
+//                         the cell on a row (span_of_row: four half-planes + the exact test for a pixel
 //                         within rounding noise of a boundary).
 //   row_segments_kernel : one thread per (frame, row, 128-px tile): the candidates' intervals resolved by
 //                         "the last cell written wins" into <= 16 sorted segments (first x, cell id), and
 //                         the owner of each lane's group of four pixels (what the pixel kernel reads).
 //   warp_fast_kernel    : CTA = 128 x 120 output pixels, warp = 128 x 15, four adjacent pixels per thread
-//                         and row.  Per row a thread looks its cell up in the segment list, evaluates
-//                         the cell's remap coordinates in float32 in box-local form (error < eps, see
-//                         mf_math.cuh) and keeps rint() only when the value is outside the rounding
-//                         band; the four footprints are adjacent, so the two source rows are read once
-//                         as 4-5 aligned words each, brought to phase 0 with funnel shifts, and the
-//                         taps are regrouped with constant-selector PRMTs for the dp2a blend.
+//                         and row.  Per row a thread reads its group's owner (one 16-bit load, requested a
+//                         row ahead), the cell's 64-byte parameter block from L1, evaluates the remap
+//                         coordinates in float32 in box-centred form (error < eps, see mf_math.cuh) and
+//                         keeps rint() only when the value is outside the rounding band; when the four
+//                         footprints are adjacent the two source rows are read once as 4-5 aligned words
+//                         each (the next row's new line is prefetched into L1), brought to phase 0 with
+//                         funnel shifts, and the taps are regrouped with constant-selector PRMTs for the
+//                         dp2a blend.
 //                         Everything else -- pixels inside the rounding band, groups that straddle a
 //                         segment, non-adjacent footprints, taps outside the frame, crop-edge
 //                         candidates, irregular cells -- is listed in the warp's shared-memory queue and
@@ -30,8 +32,7 @@
 
 namespace mf {
 
-// Member interval of every cell on every row of its support box: one thread per (frame, cell, row of the
-// box).  span_tab[(f * ncell + id) * span_rows + (y - by0)] = a | b << 16 (a > b: no member pixel;
+// Member interval of every cell on every row of its support box.  span_tab[(f * ncell + id) * span_rows + (y - by0)] = a | b << 16 (a > b: no member pixel;
 // kSpanIrregular: the row cannot be described by an interval with certainty).  Cells whose box is taller than
 // span_rows are treated as irregular by row_segments_kernel.
 static constexpr uint32_t kSpanIrregular = 0xffffffffu;

@@ -147,7 +147,8 @@ def test_jacobi_rejects_bad_definition():
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("W,H,R,C,F,amp", [(320, 180, 8, 8, 3, 2.5), (640, 360, 16, 16, 2, 3.0),
                                            (333, 217, 6, 9, 2, 2.0), (200, 120, 4, 6, 2, 15.0),
-                                           (1920, 1080, 16, 16, 1, 3.0), (1280, 720, 64, 64, 1, 1.0)])
+                                           (1920, 1080, 16, 16, 1, 3.0), (1280, 720, 64, 64, 1, 1.0),
+                                           (160, 96, 48, 80, 2, 0.15)])     # 2 x 2 px cells: candidate lists overflow
 def test_warp_matches_oracle(W, H, R, C, F, amp):
     rng = np.random.default_rng(W + R)
     frames, u, s = synth.synthetic_warp_inputs(rng, F, W, H, R, C, per_vertex=amp, per_frame=1.2 * amp)

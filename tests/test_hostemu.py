@@ -110,7 +110,7 @@ def test_warp_arithmetic_matches_spec(emu, W, H, R, C, amp, seed):
 # fast path of the warp (csrc/warp_fast.cuh): exact row spans + float32 coordinates outside the band
 # ----------------------------------------------------------------------------------------------
 FAST_CASES = [(320, 180, 8, 8, 2.5, 1), (200, 120, 4, 6, 15.0, 3), (256, 144, 16, 16, 1.0, 5), (640, 360, 16, 16, 3.0, 7),
-              (333, 217, 6, 9, 2.0, 9), (640, 360, 40, 40, 0.8, 11)]
+              (333, 217, 6, 9, 2.0, 9), (640, 360, 40, 40, 0.8, 11), (160, 96, 48, 80, 0.15, 13)]
 
 
 @pytest.mark.parametrize("W,H,R,C,amp,seed", FAST_CASES)
@@ -123,7 +123,7 @@ def test_row_spans_equal_the_membership_test_pixel_for_pixel(emu, W, H, R, C, am
     emu.emu_span_audit(P(rest), P(uu), P(ss), W, H, R, C, P(audit))
     assert audit[2] == 0, "a row span disagrees with cell_inside"
     assert audit[1] == 0 or amp > 5
-    if amp < 5:
+    if amp < 5 and W // C >= 8:
         assert audit[3] >= 0.95 * R * C
 
 
@@ -144,8 +144,10 @@ def test_fast_warp_path_matches_spec(emu, W, H, R, C, amp, seed):
     crop2 = np.zeros(4, np.int32); stats2 = np.zeros(6, np.int64)
     emu.emu_warp_frame_fast(P(src), P(rest), P(uu), P(ss), W, H, R, C, 9, 8, 7, None, P(crop2), 1, P(stats2))
     assert crop2.tolist() == crop.tolist()
-    if amp < 3:
+    if amp < 3 and W // C >= 8:
         assert stats[3] <= 0.01 * stats[4]           # (almost) no irregular row segments on mild meshes
+    if W // C < 4:
+        assert stats[3] == stats[4]                  # 2 x 2 px cells: every candidate list overflows, all rows exact
 
 
 def test_fast_warp_path_takes_most_pixels_of_a_smooth_warp(emu):
