@@ -523,30 +523,48 @@ __global__ void __launch_bounds__(kWarpThreads, MF_RESIZE_MINBLOCKS) crop_resize
     regular = regular && c1[j] == c0[j] + 1 && c0[j] + 4 <= W - 1;     // 12-byte reads stay inside the row
   }
   if (regular) {
-    RowSums A, B;
-    int ra = -1, rb = -1;
-    for (int py = y_first; py < y_end; ++py, drow += pitch) {
-      const int4 yt = __ldg(ytab + py);
-      const int r0 = top + yt.x, r1 = top + yt.y;            // warp-uniform
-      if (r0 != ra) {
-        if (r0 == rb) A = B; else resize_hsum(src + (size_t)r0 * pitch, woff, shift, wx, A);
-        ra = r0;
-      }
-      if (r1 != rb) {
-        if (r1 == ra) B = A; else resize_hsum(src + (size_t)r1 * pitch, woff, shift, wx, B);
-        rb = r1;
-      }
+    // Two row buffers whose roles (top / bottom) swap instead of being copied when the window moves down by
+    // one source row: `swapped` says which is which, and the step is instantiated once per role assignment.
+    RowSums P, Q;
+    int rp = -1, rq = -1;
+    bool swapped = false;                                    // false: P is the top row, Q the bottom row
+    auto vertical = [&](const RowSums& T, const RowSums& M, const int4& yt) {
       const uint32_t b0s = (uint32_t)yt.z << 16, b1s = (uint32_t)yt.w << 16;
       uint32_t v[kPix][3];
 #pragma unroll
       for (int j = 0; j < kPix; ++j)
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch)   // a0 + a1 <= 2049 and b0 + b1 <= 2049 bound the result by 255: no clamp needed
-          v[j][ch] = (__umulhi(b0s, A.v[j][ch]) + __umulhi(b1s, B.v[j][ch]) + 2u) >> 2;
+          v[j][ch] = (__umulhi(b0s, T.v[j][ch]) + __umulhi(b1s, M.v[j][ch]) + 2u) >> 2;
       uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
       __stcs(d32 + 0, __byte_perm(__byte_perm(v[0][0], v[0][1], 0x0040), __byte_perm(v[0][2], v[1][0], 0x0040), 0x5410));
       __stcs(d32 + 1, __byte_perm(__byte_perm(v[1][1], v[1][2], 0x0040), __byte_perm(v[2][0], v[2][1], 0x0040), 0x5410));
       __stcs(d32 + 2, __byte_perm(__byte_perm(v[2][2], v[3][0], 0x0040), __byte_perm(v[3][1], v[3][2], 0x0040), 0x5410));
+    };
+    // T holds source row rt in the top role, M holds rm in the bottom role; returns true when the roles swapped
+    auto step = [&](RowSums& T, RowSums& M, int& rt, int& rm, int r0, int r1, const int4& yt) -> bool {
+      if (r0 != rt && r0 == rm && r1 != rm) {                // the usual move: old bottom becomes top, one new row
+        resize_hsum(src + (size_t)r1 * pitch, woff, shift, wx, T);
+        rt = r1;
+        vertical(M, T, yt);
+        return true;
+      }
+      if (r0 != rt) {
+        if (r0 == rm) T = M; else resize_hsum(src + (size_t)r0 * pitch, woff, shift, wx, T);
+        rt = r0;
+      }
+      if (r1 != rm) {
+        if (r1 == rt) M = T; else resize_hsum(src + (size_t)r1 * pitch, woff, shift, wx, M);
+        rm = r1;
+      }
+      vertical(T, M, yt);
+      return false;
+    };
+    for (int py = y_first; py < y_end; ++py, drow += pitch) {
+      const int4 yt = __ldg(ytab + py);
+      const int r0 = top + yt.x, r1 = top + yt.y;            // warp-uniform
+      const bool flip = swapped ? step(Q, P, rq, rp, r0, r1, yt) : step(P, Q, rp, rq, r0, r1, yt);
+      swapped = swapped != flip;
     }
     return;
   }
