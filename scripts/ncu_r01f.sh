@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
-# ncu evidence r01e (warp fast path + rolling-row resize); run under gpurun, one GPU.  Numbers printed under ncu are never bench values.
-tag=${1:-r01e}
+# ncu evidence r01f (warp fast path + rolling-row resize); run under gpurun, one GPU.  Numbers printed under ncu are never bench values.
+tag=${1:-r01f}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_launches.stdout 2>&1
