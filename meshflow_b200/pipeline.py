@@ -242,6 +242,9 @@ class StreamedCore:
         F = int(h_frames.shape[0])
         main = torch.cuda.current_stream(dev)
         rank, _ = mfd.world_info()
+        # the chunk buffers are reused from call to call: uploads may not start before the work already queued on
+        # the caller's stream (e.g. the previous video's last warp) is done with them
+        self.copy_in.wait_stream(main)
         # 1. paths of the whole video (all-gathers / vertex-sharded solve when there are several ranks)
         tr = {k: v.to(dev, non_blocking=True) for k, v in tracks.items()}
         u_all, s_all, _ = mfd.sharded_paths(core, tr, F, definition, pair_start_host=tracks["pair_start"])

@@ -328,4 +328,28 @@ void emu_cell_fast_info(const float* vertex_xy, const double* u, const double* s
   }
 }
 
+
+// SegBuilder on its own: candidates (descending priority order as given) with intervals [a, b] on the tile
+// [x0, x1]; writes the sorted segments, returns their number (-1: more than cap) and per-pixel owners from
+// seg_owner / seg_group_owner for comparison with a brute-force resolution.
+int emu_resolve_segments(int x0, int x1, int n, const int* a, const int* b, const int* ids, int cap, unsigned* seg_out,
+                         unsigned* owner_px, unsigned* owner_group) {
+  mf::SegBuilder sb; sb.begin(x0, x1);
+  for (int k = 0; k < n && !sb.overflow && !sb.done(); ++k) {
+    const int lo = std::max(a[k], x0), hi = std::min(b[k], x1);
+    if (lo <= hi) sb.cover(lo, hi, (unsigned)ids[k], cap);
+  }
+  const int ns = sb.finish(cap);
+  if (ns < 0) return -1;
+  unsigned seg[mf::kSegMax];
+  for (int i = 0; i < mf::kSegMax; ++i) { seg[i] = i < ns ? sb.seg[i] : mf::kSegSentinel; seg_out[i] = seg[i]; }
+  for (int x = x0; x <= x1; ++x) owner_px[x - x0] = mf::seg_owner(seg, cap, x);
+  for (int g = x0; g <= x1; g += 4) {
+    bool strad;
+    const unsigned o = mf::seg_group_owner(seg, cap, g, strad);
+    owner_group[(g - x0) / 4] = strad ? mf::kSegStraddle : o;
+  }
+  return ns;
+}
+
 }  // extern "C"

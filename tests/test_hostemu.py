@@ -189,3 +189,35 @@ def test_fast_warp_path_identity_and_folded_mesh(emu):
     mx, my, _ = spec.warp_maps(W, H, sc, prune=False)
     assert np.array_equal(dst, spec.remap_fixed(src, mx, my, (0, 0, 255)))
     assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
+
+
+def test_segment_resolution_matches_brute_force(emu):
+    """'The last cell written wins': random overlapping intervals in priority order against a per-pixel loop."""
+    rng = np.random.default_rng(5)
+    x0, x1 = 256, 383
+    overflowed = 0
+    for trial in range(400):
+        n = int(rng.integers(0, 12))
+        a = rng.integers(x0 - 30, x1 + 10, n).astype(np.int32)
+        b = (a + rng.integers(-3, 90, n)).astype(np.int32)
+        ids = np.sort(rng.choice(5000, n, replace=False))[::-1].astype(np.int32)      # descending id = priority
+        cap = 8 if trial % 2 else 16
+        seg = np.zeros(16, np.uint32); opx = np.zeros(128, np.uint32); ogr = np.zeros(32, np.uint32)
+        ns = emu.emu_resolve_segments(x0, x1, n, P(a), P(b), P(ids), cap, P(seg), P(opx), P(ogr))
+        ref = np.full(128, 0xFFFF, np.uint32)
+        for k in range(n - 1, -1, -1):                       # lowest priority first, higher ones overwrite
+            lo, hi = max(int(a[k]), x0), min(int(b[k]), x1)
+            if lo <= hi:
+                ref[lo - x0:hi - x0 + 1] = ids[k]
+        changes = 1 + int((np.diff(ref.astype(np.int64)) != 0).sum())
+        if ns < 0:
+            overflowed += 1
+            assert changes > cap // 2                        # only gives up when there really are many segments
+            continue
+        assert np.array_equal(opx, ref)
+        for g in range(32):
+            grp = ref[4 * g:4 * g + 4]
+            want = 0xFFFD if (grp != grp[0]).any() else grp[0]
+            assert ogr[g] == want
+        assert (np.diff((seg[:ns] >> 16).astype(np.int64)) > 0).all() and (seg[ns:] == 0xFFFFFFFF).all()
+    assert overflowed < 200
