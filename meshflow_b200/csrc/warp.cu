@@ -40,6 +40,7 @@ static constexpr int kWarpThreads = 256; // 32 lanes x 8 rows
 #endif
 static constexpr int kFastRows = MF_FAST_ROWS;     // fast path: rows per warp (<= 16: one 64-bit mask of 4 bits per row)
 static constexpr int kFastTileH = 8 * kFastRows;   // 120: divides 720, 1080, 1440, 2160, 4320
+static_assert(kFastRows >= 1 && kFastRows <= 16, "four mask bits per row in one 64-bit word, four row bits per queue entry");
 
 __global__ void __launch_bounds__(128) cell_setup_kernel(
 
