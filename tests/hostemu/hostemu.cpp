@@ -352,4 +352,45 @@ int emu_resolve_segments(int x0, int x1, int n, const int* a, const int* b, cons
   return ns;
 }
 
+
+// Audit of the float32 remap coordinates over every member pixel of every cell with a float32 form:
+// out[0] = pixels examined, out[1] = pixels inside the rounding band (float64 path), out[2] = SAFE pixels whose
+// rint() differs from the reference's 1/32-px coordinate (must be 0); ratio[0] = largest observed
+// |float32 value - float64 value| over the cell's eps (how conservative the bound is; must stay < 1).
+void emu_fast_coord_audit(const float* vertex_xy, const double* u, const double* s, int W, int H, int R, int C,
+                          long long* out, double* ratio) {
+  std::vector<mf::Cell> cells; std::vector<mf::CellFast> fast; std::vector<mf::CellSpan> spans;
+  emu_cells_all(vertex_xy, u, s, W, H, R, C, cells, fast, spans);
+  out[0] = out[1] = out[2] = 0; ratio[0] = 0.0;
+  for (int id = 0; id < R * C; ++id) {
+    const mf::Cell& c = cells[id];
+    const mf::CellFast& cf = fast[id];
+    if (cf.thr_u < 0.0f || c.bx0 > c.bx1) continue;
+    for (int py = c.by0; py <= c.by1; ++py)
+      for (int px = c.bx0; px <= c.bx1; ++px) {
+        if (!mf::cell_inside(c, (double)px, (double)py)) continue;
+        float mx, my;
+        mf::cell_map(c, (double)px, (double)py, mx, my);
+        int ix, iy, ax, ay;
+        mf::remap_coords(mx, my, ix, iy, ax, ay);
+        const int sx_ref = ix * 32 + ax, sy_ref = iy * 32 + ay;
+        const float fy = (float)(py - cf.by0), fx = (float)(px - cf.bx0);
+        unsigned nu, nv;
+        const bool safe = mf::fast_coords(cf.a[0], cf.a[3], cf.a[6], fmaf(cf.a[1], fy, cf.a[2]), fmaf(cf.a[4], fy, cf.a[5]),
+                                          fmaf(cf.a[7], fy, cf.a[8]), fx, cf.thr_u, cf.thr_v, nu, nv);
+        out[0]++;
+        if (!safe) { out[1]++; continue; }
+        const int sx = (int)(nu - mf::kRoundMagicBits) + cf.base_x, sy = (int)(nv - mf::kRoundMagicBits) + cf.base_y;
+        if (sx != sx_ref || sy != sy_ref) out[2]++;
+        // observed error of the float32 value against the float64 map (in 1/32-px units), relative to eps = 0.5 - thr - tie
+        const float Uf = fmaf(cf.a[0], fx, fmaf(cf.a[1], fy, cf.a[2])) / fmaf(cf.a[6], fx, fmaf(cf.a[7], fy, cf.a[8]));
+        const double w = (double)px * c.Hsu[6] + (double)py * c.Hsu[7] + 1.0;
+        const double ue = 32.0 * (((double)px * c.Hsu[0] + (double)py * c.Hsu[1] + c.Hsu[2]) / w) - (double)cf.base_x;
+        const double band = 0.5 - (double)cf.thr_u;             // eps + tie radius (>= eps)
+        const double rel = fabs((double)Uf - ue) / band;
+        if (rel > ratio[0]) ratio[0] = rel;
+      }
+  }
+}
+
 }  // extern "C"

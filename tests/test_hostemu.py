@@ -221,3 +221,28 @@ def test_segment_resolution_matches_brute_force(emu):
             assert ogr[g] == want
         assert (np.diff((seg[:ns] >> 16).astype(np.int64)) > 0).all() and (seg[ns:] == 0xFFFFFFFF).all()
     assert overflowed < 200
+
+
+@pytest.mark.parametrize("W,H,R,C", [(1920, 1080, 16, 16), (3840, 2160, 16, 16), (1280, 720, 64, 64), (1920, 1080, 32, 32)])
+def test_float32_coordinates_never_disagree_outside_the_band(emu, W, H, R, C):
+    """Every member pixel of every cell, camera-like and rough meshes: a pixel the float32 path calls safe has the
+    reference's 1/32-px coordinate, and the observed float32 error stays well inside the band the cell reserves."""
+    rng = np.random.default_rng(W + R)
+    rest = spec.vertex_xy(W, H, R, C)
+    rest64 = rest.astype(np.float64)
+    total = 0
+    for trial in range(3):
+        Hm = synth.random_homography(rng, W, H, rot=0.004 * (1 + 4 * trial), scale=0.003 * (1 + 4 * trial), trans=6.0 * (1 + trial),
+                                     persp=2e-6 * (1 + trial))
+        w = rest64[:, 0] * Hm[2, 0] + rest64[:, 1] * Hm[2, 1] + 1.0
+        d = np.stack([(rest64[:, 0] * Hm[0, 0] + rest64[:, 1] * Hm[0, 1] + Hm[0, 2]) / w - rest64[:, 0],
+                      (rest64[:, 0] * Hm[1, 0] + rest64[:, 1] * Hm[1, 1] + Hm[1, 2]) / w - rest64[:, 1]], axis=1)
+        d = np.ascontiguousarray(d + rng.normal(0, 0.3 * trial, d.shape))
+        zero = np.zeros_like(d)
+        out = np.zeros(3, np.int64); ratio = np.zeros(1)
+        emu.emu_fast_coord_audit(P(rest), P(zero), P(d), W, H, R, C, P(out), P(ratio))
+        assert out[2] == 0, f"{out[2]} safe pixels with a wrong coordinate"
+        assert ratio[0] < 1.0
+        assert out[1] < 0.06 * out[0]                          # a few per cent of the pixels take the float64 path
+        total += int(out[0])
+    assert total > 2 * W * H
