@@ -10,6 +10,7 @@ still needs the compacted inliers on the host because ``cv2.findHomography`` run
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 import threading
@@ -92,14 +93,52 @@ def track_pair(early, late, subframe_rows=4, subframe_cols=4, min_features=4) ->
                       np.ascontiguousarray(np.concatenate(keep_raw), dtype=np.uint8), hom)
 
 
-def track_all_pairs(frames_a, frames_b, subframe_rows=4, subframe_cols=4, min_features=4, workers=None):
+def default_workers() -> int:
+    """One worker per host core this process may use (the pairs are independent; OpenCV releases the GIL)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(1, min(64, n))
+
+
+_cv_threads_lock = threading.Lock()
+_cv_threads_depth = 0
+_cv_threads_saved = None
+
+
+@contextlib.contextmanager
+def single_threaded_opencv():
+    """While many pairs are tracked concurrently each OpenCV call runs on its caller's thread only:
+    the pool already occupies every core, and OpenCV's own parallel_for on quarter-frame subimages
+    would only oversubscribe them.  Results do not depend on OpenCV's thread count."""
+    global _cv_threads_depth, _cv_threads_saved
+    with _cv_threads_lock:
+        if _cv_threads_depth == 0:
+            _cv_threads_saved = cv2.getNumThreads()
+            cv2.setNumThreads(1)
+        _cv_threads_depth += 1
+    try:
+        yield
+    finally:
+        with _cv_threads_lock:
+            _cv_threads_depth -= 1
+            if _cv_threads_depth == 0:
+                cv2.setNumThreads(_cv_threads_saved)
+
+
+def track_all_pairs(frames_a, frames_b, subframe_rows=4, subframe_cols=4, min_features=4, workers=None, pool=None):
     """``track_pair`` over many independent pairs on a thread pool (OpenCV releases the GIL).
-    Results are returned in pair order and do not depend on the number of workers."""
+    Results are returned in pair order and do not depend on the number of workers.  ``pool``: an
+    existing ``ThreadPoolExecutor`` to run on (else a temporary one with ``workers`` threads)."""
     n = len(frames_a)
     if workers is None:
-        workers = min(32, os.cpu_count() or 1)
+        workers = default_workers()
     job = lambda i: track_pair(frames_a[i], frames_b[i], subframe_rows, subframe_cols, min_features)
-    if workers <= 1 or n <= 1:
+    if n <= 1 or (pool is None and workers <= 1):
         return [job(i) for i in range(n)]
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        return list(pool.map(job, range(n)))
+    with single_threaded_opencv():
+        if pool is not None:
+            return list(pool.map(job, range(n)))
+        with ThreadPoolExecutor(max_workers=workers) as own:
+            return list(own.map(job, range(n)))

@@ -9,15 +9,24 @@ reference.  What changed is where the three data-parallel stages run:
 
 * vertex-motion estimation  (mfs.py:236-452)  -> ``mf_vertex_motion`` + ``mf_prefix_displacements``
 * Jacobi path optimisation  (mfs.py:632-878)  -> ``mf_jacobi_solve``
-* mesh warp + crop          (mfs.py:909-1157) -> ``mf_warp_frames`` + ``mf_crop_resize``
+* mesh warp + crop          (mfs.py:909-1157) -> ``mf_warp_prepare`` + ``mf_warp_resize_frames``
 
 all hand-written sm_100a kernels behind the C ABI in ``include/meshflow_b200.h``.  Video decode,
 FAST/LK/RANSAC feature matching, the two OpenCV-derived metrics and video encode stay host OpenCV
 code, as in the reference, so both implementations see identical correspondences.  There is no CPU
 fallback for the three stages.
+
+Host / device overlap: the OpenCV front end runs on a persistent thread pool, one
+job per frame pair; while it runs, the frames are staged into pinned memory and uploaded; once the
+paths and the crop rectangle are known the pixel pass runs chunk by chunk, and the metric tracking
+(mfs.py:1160-1212) of a chunk's frames is handed to the pool the moment the chunk's device-to-host
+copy has landed, so it overlaps the rest of the pixel pass.
 """
 from __future__ import annotations
 
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
 
 import cv2
 import numpy as np
@@ -42,7 +51,8 @@ class MeshFlowStabilizer:
                  homography_min_number_corresponding_features=4,
                  temporal_smoothing_radius=10, optimization_num_iterations=100,
                  color_outside_image_area_bgr=(0, 0, 255),
-                 visualize=False, *, device=None, host_workers=None, chunk_frames=16):
+                 visualize=False, *, device=None, host_workers=None, chunk_frames=16, distributed=False,
+                 resident_limit_bytes=16 << 30):
         self.mesh_col_count = mesh_col_count
         self.mesh_row_count = mesh_row_count
         self.mesh_outlier_subframe_row_count = mesh_outlier_subframe_row_count
@@ -59,7 +69,16 @@ class MeshFlowStabilizer:
         self.device = device
         self.host_workers = host_workers
         self.chunk_frames = chunk_frames
+        # distributed=True: under torchrun (one process per GPU, torch.distributed initialised) stabilize() shards
+        # the video's frames over the ranks.  Off by default: a process that merely runs under torchrun
+        # stabilizes its own whole video.
+        self.distributed = bool(distributed)
+        self.resident_limit_bytes = int(resident_limit_bytes)
         self._cores = {}
+        self._streamed = {}
+        self._pool = None
+        self._pinned = {}
+        self.last_timings = {}
 
     # ------------------------------------------------------------------------------------------
     # public entry point (mfs.py:102-169)
@@ -67,52 +86,189 @@ class MeshFlowStabilizer:
     def stabilize(self, input_path, output_path,
                   adaptive_weights_definition=ADAPTIVE_WEIGHTS_DEFINITION_ORIGINAL):
         self._validate_definition(adaptive_weights_definition)
+        plan = self._plan_for_video(input_path) if self.distributed else None
+        if plan is not None and plan.world > 1:
+            return self._stabilize_sharded(input_path, output_path, adaptive_weights_definition, plan)
+        t0 = time.perf_counter()
         frames, num_frames, fps, codec = self._get_unstabilized_frames_and_video_features(input_path)
-        result = self.stabilize_frames(frames, adaptive_weights_definition)
+        t_decode = time.perf_counter() - t0
+        result = self.stabilize_frames(frames, adaptive_weights_definition, reuse_output=True)
+        t0 = time.perf_counter()
         self._write_stabilized_video(output_path, num_frames, fps, codec, result["cropped_frames"])
+        self.last_timings = dict(result["timings"], decode=t_decode, encode=time.perf_counter() - t0)
         if self.visualize:
             self._display_unstablilized_and_cropped_video_loop(num_frames, fps, frames, result["cropped_frames"])
         return (result["cropping_ratio"], result["distortion_score"], result["stability_score"])
 
     def stabilize_frames(self, unstabilized_frames, adaptive_weights_definition=ADAPTIVE_WEIGHTS_DEFINITION_ORIGINAL,
-                         with_metrics=True):
+                         with_metrics=True, plan=None, lookahead_frame=None, reuse_output=False):
         """``stabilize()`` on in-memory frames: everything between decode and encode, device resident
         between the stages.  Returns a dict with the cropped frames, the crop rectangle, ``u``,
-        ``homographies``, ``s`` (NumPy) and the three metrics."""
+        ``homographies``, ``s`` (NumPy, whole video), the three metrics and per-stage wall times.
+
+        ``plan`` (a ``distributed.ShardPlan``) + ``lookahead_frame`` (the next rank's first frame; None on
+        the rank that owns the video's last frame): the frames are this rank's contiguous shard of a longer
+        video; paths, crop rectangle and metrics are those of the whole video on every rank.
+
+        ``reuse_output=True`` writes the cropped frames into a pinned buffer that this object keeps and
+        reuses: the returned frames are then only valid until the next call (``stabilize()`` works this
+        way -- it encodes them right away).  By default the frames live in a buffer of their own."""
+        from . import distributed as mfd
         self._validate_definition(adaptive_weights_definition)
-        num_frames = len(unstabilized_frames)
-        if num_frames < 2:
-            raise ValueError("need at least two frames to stabilize")
-        height, width = unstabilized_frames[0].shape[:2]
+        t_start = time.perf_counter()
+        timings = {}
+        frames = unstabilized_frames
+        F = len(frames)
+        sharded = plan is not None and plan.world > 1
+        if not sharded:
+            plan = None
+            if F < 2:
+                raise ValueError("need at least two frames to stabilize")
+        elif F == 0:
+            raise ValueError("a rank without frames cannot take part (use fewer ranks than frames)")
+        height, width = frames[0].shape[:2]
         core = self._core(width, height)
-        tracks = self._track(unstabilized_frames[:-1], unstabilized_frames[1:])
-        packed = self.pack_tracks(tracks)
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        h_tracks = {k: pin(packed[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
-        h_tracks["homographies"] = pin(packed["homographies"].reshape(-1, 9))
-        h_frames = torch.empty((num_frames, height, width, 3), dtype=torch.uint8, pin_memory=True)
-        view = h_frames.numpy()
-        for i, f in enumerate(unstabilized_frames):
-            view[i] = f
-        h_out = torch.empty_like(h_frames, pin_memory=True)
-        # host buffers in, host buffers out: copies overlap the kernels (pipeline.StreamedCore)
-        crop_enc, u_d, s_d = StreamedCore(core, self.chunk_frames).run(h_frames, h_tracks, h_out,
-                                                                       adaptive_weights_definition)
-        stability = core.stability_score(s_d) if with_metrics else None
-        crop = self._crop_tuple(crop_enc)                    # synchronises
-        torch.cuda.synchronize(core.device)
-        self._check_crop(crop, width, height)
-        cropped = h_out.numpy()
-        cropped_frames = [cropped[i] for i in range(num_frames)]
-        homs = np.empty((num_frames, 3, 3))
-        homs[:-1] = packed["homographies"]
-        homs[-1] = np.identity(3)                            # mfs.py:273-274
-        out = dict(cropped_frames=cropped_frames, crop_boundaries=crop, u=u_d.cpu().numpy(), homographies=homs,
-                   s=s_d.cpu().numpy())
-        if with_metrics:
-            cr, ds = self._compute_cropping_ratio_and_distortion_score(num_frames, unstabilized_frames, cropped_frames)
-            out.update(cropping_ratio=cr, distortion_score=ds, stability_score=np.float64(stability.item()))
+        streamed = self._streamed_for(core)
+        dev = core.device
+        pool = self._thread_pool()
+        total_frames = plan.total_frames if sharded else F
+        # -- 1. host front end on the pool: one job per frame pair that starts at one of this rank's frames
+        late = list(frames[1:]) + ([lookahead_frame] if (sharded and lookahead_frame is not None) else [])
+        n_pairs = len(late)
+        if sharded and n_pairs < plan.pairs_needed():
+            raise ValueError("this rank's last frame needs the next rank's first frame (lookahead_frame)")
+        track = lambda a, b: host_features.track_pair(
+            a, b, self.mesh_outlier_subframe_row_count, self.mesh_outlier_subframe_col_count,
+            self.homography_min_number_corresponding_features)
+        with host_features.single_threaded_opencv():
+            futures = [pool.submit(track, frames[i], late[i]) for i in range(n_pairs)]
+            # -- 2. meanwhile: frames -> pinned memory -> device (resident when they fit, else streamed later)
+            t0 = time.perf_counter()
+            frame_bytes = height * width * 3
+            h_in = self._pinned_buffer("in", (F, height, width, 3))
+            h_out = (self._pinned_buffer("out", (F, height, width, 3)) if reuse_output
+                     else torch.empty((F, height, width, 3), dtype=torch.uint8, pin_memory=True))
+            resident = F * frame_bytes <= self.resident_limit_bytes
+            view = h_in.numpy()
+            with torch.cuda.device(dev):
+                main = torch.cuda.current_stream(dev)
+                d_frames = torch.empty((F, height, width, 3), dtype=torch.uint8, device=dev) if resident else None
+                for f0 in range(0, F, self.chunk_frames):
+                    n = min(self.chunk_frames, F - f0)
+                    for i in range(f0, f0 + n):
+                        view[i] = frames[i]
+                    if resident:
+                        with torch.cuda.stream(streamed.copy_in):
+                            d_frames[f0:f0 + n].copy_(h_in[f0:f0 + n], non_blocking=True)
+                if resident:
+                    main.wait_stream(streamed.copy_in)
+            timings["stage_frames"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            tracks = [f.result() for f in futures]
+            timings["track_wait"] = time.perf_counter() - t0
+            # -- 3. paths + crop rectangle, then the pixel pass chunk by chunk; metric tracking per landed chunk
+            t0 = time.perf_counter()
+            packed = self.pack_tracks(tracks)
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            h_tracks = {k: pin(packed[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
+            h_tracks["homographies"] = pin(packed["homographies"].reshape(-1, 9))
+            cropped = h_out.numpy()
+            metric_futures = []
+            if with_metrics:
+                def on_chunk(f0, n):
+                    metric_futures.extend(pool.submit(track, frames[i], cropped[i]) for i in range(f0, f0 + n))
+            else:
+                on_chunk = None
+            crop_enc, u_d, s_d, homs_d = streamed.run(h_in, h_tracks, h_out, adaptive_weights_definition, plan=plan,
+                                                      d_frames=d_frames, on_chunk_landed=on_chunk, return_homographies=True)
+            stability = core.stability_score(s_d) if with_metrics else None
+            crop = self._crop_tuple(crop_enc)                    # synchronises
+            torch.cuda.synchronize(dev)
+            self._check_crop(crop, width, height)
+            timings["device"] = time.perf_counter() - t0
+            cropped_frames = [cropped[i] for i in range(F)]
+            out = dict(cropped_frames=cropped_frames, crop_boundaries=crop, u=u_d.cpu().numpy(),
+                       homographies=homs_d.cpu().numpy().reshape(total_frames, 3, 3), s=s_d.cpu().numpy())
+            if with_metrics:
+                t0 = time.perf_counter()
+                ratios, scores = self._ratios_and_scores([f.result() for f in metric_futures])
+                if sharded:
+                    ratios, scores = self._gather_metric_arrays(ratios, scores, plan, dev)
+                timings["metrics_wait"] = time.perf_counter() - t0
+                out.update(cropping_ratio=np.mean(ratios), distortion_score=np.min(scores),
+                           stability_score=np.float64(stability.item()))
+        timings["total"] = time.perf_counter() - t_start
+        out["timings"] = timings
+        self.last_timings = timings
         return out
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU: frames sharded over the ranks of torch.distributed (opt-in: distributed=True)
+    # ------------------------------------------------------------------------------------------
+    def _plan_for_video(self, input_path):
+        import torch.distributed as dist
+        from . import distributed as mfd
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+        video = cv2.VideoCapture(input_path)
+        num_frames = int(video.get(cv2.CAP_PROP_FRAME_COUNT))
+        video.release()
+        return mfd.ShardPlan.even(num_frames)
+
+    def _stabilize_sharded(self, input_path, output_path, definition, plan):
+        """Every rank decodes the file but keeps only its contiguous frame range (+ one look-ahead frame),
+        tracks its own pairs, and runs the sharded core; cropped frames meet in one host shared-memory
+        buffer (the ranks of one box share the host), rank 0 encodes.  Every rank returns the tuple."""
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        begin = plan.first_frame
+        end = begin + plan.local_frames
+        video = cv2.VideoCapture(input_path)
+        num_frames = int(video.get(cv2.CAP_PROP_FRAME_COUNT))
+        fps = video.get(cv2.CAP_PROP_FPS)
+        codec = int(video.get(cv2.CAP_PROP_FOURCC))
+        frames, lookahead = [], None
+        for frame_index in range(min(end + 1, num_frames)):
+            frame = self._get_next_frame(video)
+            if frame is None:
+                raise IOError(f'Video at <{input_path}> did not have frame {frame_index} of '
+                              f'{num_frames} (indexed from 0).')
+            if begin <= frame_index < end:
+                frames.append(frame)
+            elif frame_index == end:
+                lookahead = frame
+        video.release()
+        result = self.stabilize_frames(frames, definition, plan=plan, lookahead_frame=lookahead, reuse_output=True)
+        h, w = frames[0].shape[:2]
+        # cropped frames of all ranks -> one shared host buffer, in frame order
+        names = [None]
+        shm = None
+        if plan.rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=num_frames * h * w * 3)
+            names[0] = shm.name
+        dist.broadcast_object_list(names, src=0, group=plan.group)
+        if plan.rank != 0:
+            shm = shared_memory.SharedMemory(name=names[0])
+        whole = np.ndarray((num_frames, h, w, 3), dtype=np.uint8, buffer=shm.buf)
+        for i, f in enumerate(result["cropped_frames"]):
+            whole[begin + i] = f
+        dist.barrier(group=plan.group)
+        if plan.rank == 0:
+            self._write_stabilized_video(output_path, num_frames, fps, codec, whole)
+        dist.barrier(group=plan.group)
+        del whole
+        shm.close()
+        if plan.rank == 0:
+            shm.unlink()
+        return (result["cropping_ratio"], result["distortion_score"], result["stability_score"])
+
+    @staticmethod
+    def _gather_metric_arrays(ratios, scores, plan, dev):
+        """Per-frame metric values of every rank, in frame order, on every rank."""
+        from . import distributed as mfd
+        local = torch.from_numpy(np.stack([ratios, scores], axis=1)).to(dev)       # [F_local, 2] float32
+        allv = mfd.gather_velocities(local, list(plan.frames), plan.group).cpu().numpy()
+        return np.ascontiguousarray(allv[:, 0]), np.ascontiguousarray(allv[:, 1])
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -143,11 +299,38 @@ class MeshFlowStabilizer:
             self._cores[key] = core
         return core
 
+    def _streamed_for(self, core) -> StreamedCore:
+        sc = self._streamed.get(id(core))
+        if sc is None or sc.chunk != int(self.chunk_frames):
+            sc = StreamedCore(core, self.chunk_frames)
+            self._streamed[id(core)] = sc
+        return sc
+
+    def _thread_pool(self) -> ThreadPoolExecutor:
+        if self._pool is None:
+            workers = self.host_workers
+            if workers is None:
+                workers = host_features.default_workers()
+            self._pool = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="meshflow-host")
+        return self._pool
+
+    def _pinned_buffer(self, name, shape):
+        """Pinned staging buffers live as long as the stabilizer and are reused by later calls of the same
+        size (page-locking ~2 GB costs about as much as the whole GPU pass)."""
+        key = (name, tuple(shape))
+        buf = self._pinned.get(key)
+        if buf is None:
+            for k in [k for k in self._pinned if k[0] == name]:
+                del self._pinned[k]
+            buf = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+            self._pinned[key] = buf
+        return buf
+
     def _track(self, early_frames, late_frames):
         return host_features.track_all_pairs(
             early_frames, late_frames, self.mesh_outlier_subframe_row_count,
             self.mesh_outlier_subframe_col_count, self.homography_min_number_corresponding_features,
-            workers=self.host_workers)
+            workers=self.host_workers, pool=self._thread_pool())
 
     @staticmethod
     def _upload_frames(core, frames):
@@ -167,7 +350,8 @@ class MeshFlowStabilizer:
         np.cumsum(counts, out=start[1:])
         cat = lambda name, dt, tail: (np.concatenate([getattr(t, name) for t in tracks]).astype(dt, copy=False)
                                       if len(tracks) else np.zeros((0,) + tail, dt))
-        homs = np.stack([t.homography for t in tracks]).astype(np.float64)
+        homs = (np.stack([t.homography for t in tracks]).astype(np.float64) if len(tracks)
+                else np.zeros((0, 3, 3), np.float64))
         return dict(early=cat("early_xy", np.float32, (2,)), late=cat("late_xy", np.float32, (2,)),
                     offset=cat("offset_xy", np.int32, (2,)), keep=cat("keep", np.uint8, ()),
                     pair_start=start, homographies=homs, max_pair=int(counts.max()) if len(counts) else 0)
@@ -202,6 +386,20 @@ class MeshFlowStabilizer:
     def _crop_tuple(combined):
         l, t, nr, nb = (int(v) for v in combined.tolist())
         return (np.int64(l), np.int64(t), np.int64(-nr), np.int64(-nb))
+
+    @staticmethod
+    def _ratios_and_scores(tracks):
+        """mfs.py:1199-1210 on the homographies of already tracked (unstabilized, cropped) pairs."""
+        cropping_ratios = np.empty((len(tracks)), dtype=np.float32)
+        distortion_scores = np.empty((len(tracks)), dtype=np.float32)
+        for i, t in enumerate(tracks):
+            hom = t.homography
+            cropping_ratios[i] = 1 / (hom[0][0] * hom[1][1])
+            affine = np.copy(hom)
+            affine[2] = [0, 0, 1]
+            mags = np.sort(np.abs(np.linalg.eigvals(affine)))
+            distortion_scores[i] = mags[-2] / mags[-1]
+        return cropping_ratios, distortion_scores
 
     # ------------------------------------------------------------------------------------------
     # reference-named stage methods (NumPy in / NumPy out)
@@ -298,15 +496,7 @@ class MeshFlowStabilizer:
     def _compute_cropping_ratio_and_distortion_score(self, num_frames, unstabilized_frames, cropped_frames):
         """mfs.py:1160-1212 (host OpenCV; the per-frame matching runs on the thread pool)."""
         tracks = self._track(unstabilized_frames[:num_frames], cropped_frames[:num_frames])
-        cropping_ratios = np.empty((num_frames), dtype=np.float32)
-        distortion_scores = np.empty((num_frames), dtype=np.float32)
-        for i, t in enumerate(tracks):
-            hom = t.homography
-            cropping_ratios[i] = 1 / (hom[0][0] * hom[1][1])
-            affine = np.copy(hom)
-            affine[2] = [0, 0, 1]
-            mags = np.sort(np.abs(np.linalg.eigvals(affine)))
-            distortion_scores[i] = mags[-2] / mags[-1]
+        cropping_ratios, distortion_scores = self._ratios_and_scores(tracks)
         return (np.mean(cropping_ratios), np.min(distortion_scores))
 
     def _compute_stability_score(self, num_frames, vertex_stabilized_displacements_by_frame_index):

@@ -142,10 +142,25 @@ def _gloo_worker(rank, world, port_no, tmp):
         g = torch.Generator().manual_seed(5)
         V, F = 13, 9
         vel_all = torch.randn((F - 1, V, 2), generator=g)
-        counts = [d.frame_shard(F - 1, world, r)[1] - d.frame_shard(F - 1, world, r)[0] for r in range(world)]
-        b, e = d.frame_shard(F - 1, world, rank)
-        got = d.gather_velocities(vel_all[b:e].clone(), counts)
-        assert torch.equal(got, vel_all)
+        homs_all = torch.randn((F - 1, 9), generator=g, dtype=torch.float64)
+        # ragged plan: rank 0 owns 5 frames, rank 1 owns 4 (the last of them ends the video: 3 pairs)
+        plan = d.ShardPlan(rank, world, [5, 4])
+        assert plan.total_frames == F and [plan.pairs_needed(r) for r in range(world)] == [5, 3]
+        assert plan.first_frame == (0 if rank == 0 else 5)
+        plan.validate(frames_local=plan.local_frames, pairs_local=plan.pairs_needed())
+        counts = [plan.pairs_needed(r) for r in range(world)]
+        b = plan.first_frame
+        mine_v = vel_all[b:b + counts[rank]].clone()
+        mine_h = homs_all[b:b + counts[rank]].clone()
+        assert torch.equal(d.gather_velocities(mine_v, counts), vel_all)
+        gv, gh = d.gather_pairs(mine_v, mine_h, counts)                  # one packed exchange
+        assert torch.equal(gv, vel_all) and torch.equal(gh, homs_all) and gv.dtype == torch.float32
+        # a rank that supplies too few pairs, or disagrees about the plan, fails loudly
+        with pytest.raises(ValueError):
+            plan.validate(frames_local=plan.local_frames, pairs_local=plan.pairs_needed() - 1)
+        bad = d.ShardPlan(rank, world, [5, 4] if rank == 0 else [4, 5])
+        with pytest.raises(ValueError):
+            bad.validate(frames_local=bad.local_frames, pairs_local=9)
         s_true = torch.randn((F, V, 2), generator=g, dtype=torch.float64)
         v0, v1, _ = d.vertex_shard(V, world, rank)
         mine = torch.full((F, V, 2), float("nan"), dtype=torch.float64)
@@ -153,8 +168,11 @@ def _gloo_worker(rank, world, port_no, tmp):
         assert torch.equal(d.gather_paths(mine, V), s_true)
         per_rank = torch.tensor([[5, 2, -600, -340], [9, 1, -610, -330]], dtype=torch.int32)
         enc = per_rank[rank % 2].clone()
-        d.reduce_crop(enc)
+        d.reduce_crop(enc, plan)
         assert enc.tolist() == [9, 2, -600, -330]
+        alone = per_rank[rank % 2].clone()
+        d.reduce_crop(alone, None)                                       # no plan: not sharded, nothing exchanged
+        assert alone.tolist() == per_rank[rank % 2].tolist()
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

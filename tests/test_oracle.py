@@ -91,6 +91,22 @@ def test_spec_matches_port_on_seeded_inputs():
         assert np.array_equal(vp, spec.vertex_velocities(e, l, tr["homographies"][q], W, H, R, C, 10, 10))
 
 
+def test_spec_matches_port_at_the_bench_geometry():
+    """c2 geometry (1920x1080, 16x16 mesh), one frame: the per-element spec the GPU tests compare against
+    == the cv2-based port (which is pinned bit for bit to the unmodified reference): maps, pixels, crop,
+    and the resized crop.  Closes the chain GPU == spec == port == reference at the size bench.py runs."""
+    rng = np.random.default_rng(1080)
+    W, H, R, C = 1920, 1080, 16, 16
+    frames, u, s = synth.synthetic_warp_inputs(rng, 1, W, H, R, C, per_vertex=2.5, per_frame=3.0)
+    p = port.Params(mesh_row_count=R, mesh_col_count=C)
+    a, ca, ma, _ = port.warp_frames_and_crop(p, list(frames), u, s, return_maps=True)
+    b, cb, mb, _ = spec.warp_stage(list(frames), u, s, R, C, (0, 0, 255), return_maps=True)
+    assert np.array_equal(ma[0][0], mb[0][0]) and np.array_equal(ma[0][1], mb[0][1])
+    assert np.array_equal(a[0], b[0])
+    assert tuple(int(v) for v in ca) == tuple(cb)
+    assert np.array_equal(port.crop_frames(a, ca)[0], spec.crop_stage(b, cb)[0])
+
+
 def test_resize_model_matches_opencv():
     import cv2
     rng = np.random.default_rng(9)
