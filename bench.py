@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the streamed (e2e) schedule")
+    ap.add_argument("--pixel-path", default="fused", choices=["fused", "two-kernel"],
+                    help="fused = prepare (tables + crop) -> one warp+crop+resize kernel; two-kernel = round-1 sequence")
     return ap.parse_args()
 
 
@@ -239,24 +241,35 @@ def run_b200(args):
     ident = torch.eye(3, dtype=torch.float64, device=dev).reshape(1, 9)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_names = ["paths (vertex motion + prefix + Jacobi + exchanges)", "warp", "crop_resize", "stability"]
+    fused = args.pixel_path == "fused"
+    stage_names = (["paths (vertex motion + prefix + Jacobi + exchanges)", "prepare (cells, spans, segments, crop edges)",
+                    "warp", "stability"] if fused else
+                   ["paths (vertex motion + prefix + Jacobi + exchanges)", "warp", "crop_resize", "stability"])
 
     from meshflow_b200 import StreamedCore, distributed as mfd
     host_pair_start = packed["pair_start"]
+    plan = mfd.ShardPlan(rank, world, [F] * world) if world > 1 else None
 
     def hot_path(tr, frames_d, out_d, marks=None):
         def mark():
             if marks is not None:
                 e = ev(); e.record(); marks.append(e)
         mark()
-        u, s, _ = mfd.sharded_paths(core, tr, F, args.definition, pair_start_host=host_pair_start)
+        u, s, _ = mfd.sharded_paths(core, tr, F, args.definition, pair_start_host=host_pair_start, plan=plan)
         mark()
         lo = rank * F
-        _, crop_pf = core.warp_frames(frames_d, u[lo:lo + F], s[lo:lo + F], out=d_stab)
-        mark()
-        enc = mfd.reduce_crop(core.combine_crop(crop_pf))
-        core.crop_resize_device(d_stab, enc, out=out_d)
-        mark()
+        if fused:
+            crop_pf, tables = core.warp_prepare(u[lo:lo + F], s[lo:lo + F])
+            mark()
+            enc = mfd.reduce_crop(core.combine_crop(crop_pf), plan)
+            core.warp_resize_frames(frames_d, enc, tables, 0, out=out_d)
+            mark()
+        else:
+            _, crop_pf = core.warp_frames(frames_d, u[lo:lo + F], s[lo:lo + F], out=d_stab)
+            mark()
+            enc = mfd.reduce_crop(core.combine_crop(crop_pf), plan)
+            core.crop_resize_device(d_stab, enc, out=out_d)
+            mark()
         score = core.stability_score(s)
         mark()
         return enc, score
@@ -295,7 +308,7 @@ def run_b200(args):
 
     def e2e_step():
         # pinned host frames + tracks in, pinned host frames out; copies overlap the kernels
-        enc, u, s = streamed.run(h_frames, h_tracks, h_out, args.definition)
+        enc, u, s = streamed.run(h_frames, h_tracks, h_out, args.definition, plan=plan)
         score = core.stability_score(s)
         return enc, score.item()           # device -> host read of the step's result (synchronises)
 
@@ -338,7 +351,7 @@ def run_b200(args):
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_1080p_frame"] * F * (W * H) / (1920.0 * 1080.0)
         traffic_src = tj["source"]
-    resize_gbs = warp_bytes / (stage_ms["crop_resize"] / 1e3) / 1e9
+    resize_gbs = warp_bytes / (stage_ms["crop_resize"] / 1e3) / 1e9 if "crop_resize" in stage_ms else None
     out = {
         "metric": "stabilized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

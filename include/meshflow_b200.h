@@ -28,6 +28,13 @@
 extern "C" {
 #endif
 
+/* Only the entry points below are exported: the library is built with -fvisibility=hidden. */
+#if defined(__GNUC__)
+#define MF_API __attribute__((visibility("default")))
+#else
+#define MF_API
+#endif
+
 #define MF_OK 0
 #define MF_E_INVALID (-1)   /* bad argument (null pointer, non-positive size, unknown definition) */
 #define MF_E_WORKSPACE (-2) /* workspace too small */
@@ -35,10 +42,10 @@ extern "C" {
 #define MF_E_UNSUPPORTED (-4) /* size outside what the kernels are built for */
 
 /* Library / build identification.  mf_version() = 10000*major + 100*minor + patch. */
-int mf_version(void);
+MF_API int mf_version(void);
 /* Compute capability the embedded cubin was built for (100 for sm_100a). */
-int mf_built_for_sm(void);
-const char* mf_last_error(void);
+MF_API int mf_built_for_sm(void);
+MF_API const char* mf_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------
  * (1) Vertex-motion estimation -- replaces _get_unstabilized_vertex_velocities (mfs.py:287-362) minus
@@ -63,8 +70,8 @@ const char* mf_last_error(void);
  *   assign_count_out  : optional [P,V] int32, number of features assigned to each vertex (parity of
  *                       the feature->vertex assignment); may be NULL
  * ---------------------------------------------------------------------------------------------- */
-size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int C);
-int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t* offset_xy,
+MF_API size_t mf_vertex_motion_workspace_bytes(int64_t N, int P, int R, int C);
+MF_API int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t* offset_xy,
                      const uint8_t* keep, const int32_t* pair_start, const int32_t* pair_start_host,
                      int64_t N, int P,
                      const double* homographies, const float* vertex_xy,
@@ -75,7 +82,7 @@ int mf_vertex_motion(const float* early_xy, const float* late_xy, const int32_t*
 /* disp[0] = 0, disp[t+1] = disp[t] + (double)vel[t]  -- sequential float64 scan (mfs.py:271, 281).
  *   vel: [P, n] float32, disp: [P+1, n] float64, n = 2V.  An optional `disp0` [n] float64 seeds
  *   disp[0] (frame-sharded callers chain shards with it); NULL means zeros. */
-int mf_prefix_displacements(const float* vel, const double* disp0, double* disp, int P, int64_t n,
+MF_API int mf_prefix_displacements(const float* vel, const double* disp0, double* disp, int P, int64_t n,
                             void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -88,8 +95,8 @@ int mf_prefix_displacements(const float* vel, const double* disp0, double* disp,
  *   homographies  : [F,9] float64 (last one identity, mfs.py:273-274)
  *   lambda_out    : optional [F] float64 copy of the adaptive weights; may be NULL
  * ---------------------------------------------------------------------------------------------- */
-size_t mf_jacobi_workspace_bytes(int F, int64_t n_sys);
-int mf_jacobi_solve(const double* u, const double* homographies, double* s, int F, int64_t n_sys,
+MF_API size_t mf_jacobi_workspace_bytes(int F, int64_t n_sys);
+MF_API int mf_jacobi_solve(const double* u, const double* homographies, double* s, int F, int64_t n_sys,
                     int64_t sys_begin, int64_t sys_end, int W, int H, int radius, int iterations,
                     int definition, double* lambda_out, void* workspace, size_t workspace_bytes,
                     void* stream);
@@ -109,24 +116,45 @@ int mf_jacobi_solve(const double* u, const double* homographies, double* s, int 
  *                 csrc/warp_fast.cuh) -- same frames_out and crop_out, bit for bit.  Environment switches
  *                 for A/B runs: MF_WARP_GENERIC=1, MF_RESIZE_GENERIC=1.
  * ---------------------------------------------------------------------------------------------- */
-size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C);
-int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s, const float* vertex_xy,
+MF_API size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C);
+MF_API int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s, const float* vertex_xy,
                    int nf, int W, int H, int R, int C, int border_b, int border_g, int border_r,
                    uint8_t* frames_out, int32_t* crop_out, float* map_out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
-/* Pass A of the streamed schedule: the per-frame crop edges of mf_warp_frames WITHOUT touching a
- * pixel (the remap coordinates depend on the vertex paths only).  With the crop rectangle of the
- * whole video known up front, warp -> crop/resize can run chunk by chunk while frames are still being
- * uploaded and results downloaded.  Same crop_out as mf_warp_frames, same workspace size. */
-int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H,
+/* Pass A of the streamed schedule: everything about the warp that depends on the vertex paths only -- the cell
+ * homographies, the exact member interval of every cell on every output row, the row segments ("the last
+ * cell written wins", mfs.py:1060-1061) and, from the segments of the border cells, the per-frame crop edges
+ * (mfs.py:1075-1098) by a closed-form band search: no pixel is read.  With the crop rectangle of the whole
+ * video known up front, pass B (mf_warp_resize_frames) runs chunk by chunk while frames are still being
+ * uploaded and results downloaded.  Same crop_out as mf_warp_frames, same workspace size; the tables stay in
+ * `workspace` for mf_warp_resize_frames.  mf_warp_crop_bounds is the round-1 name of the same call. */
+MF_API int mf_warp_prepare(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H,
+                           int R, int C, int32_t* crop_out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+MF_API int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H,
                         int R, int C, int32_t* crop_out, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Pass B, fused: _get_stabilized_frames_and_crop_boundaries' remap (mfs.py:1063-1069) followed by
+ * _crop_frames (mfs.py:1111-1157) in ONE kernel.  A thread block produces the stabilized pixels one tile of
+ * the final frame needs into shared memory and resizes from there: the stabilized frame never exists in
+ * DRAM and pixels outside the crop rectangle are never computed.  Output identical to
+ * mf_warp_frames + mf_crop_resize_device.
+ *   frames_in     : [nf, H, W, 3] uint8, frames first_frame .. first_frame + nf - 1 of the prepared video
+ *   workspace     : the workspace mf_warp_prepare filled for `table_frames` frames (first_frame + nf <= table_frames)
+ *   crop_enc      : device int32[4] = [left, top, -right, -bottom] (mf_crop_combine, all-reduced when sharded)
+ *   resize_workspace : mf_crop_resize_workspace_bytes(W, H) bytes
+ * Returns MF_E_UNSUPPORTED for frames too small for the row-segment tables (W < 16): use the two calls. */
+MF_API int mf_warp_resize_frames(const uint8_t* frames_in, int nf, int first_frame, int table_frames, int W, int H,
+                                 int R, int C, int border_b, int border_g, int border_r, const int32_t* crop_enc,
+                                 uint8_t* frames_out, void* workspace, size_t workspace_bytes,
+                                 void* resize_workspace, size_t resize_workspace_bytes, void* stream);
+
 /* Crop rectangle (inclusive) stretched back to W x H -- replaces _crop_frames (mfs.py:1111-1157);
  * cv2.resize INTER_LINEAR 11-bit fixed point. */
-size_t mf_crop_resize_workspace_bytes(int W, int H);
-int mf_crop_resize(const uint8_t* frames_in, int nf, int W, int H, int left, int top, int right,
+MF_API size_t mf_crop_resize_workspace_bytes(int W, int H);
+MF_API int mf_crop_resize(const uint8_t* frames_in, int nf, int W, int H, int left, int top, int right,
                    int bottom, uint8_t* frames_out, void* workspace, size_t workspace_bytes,
                    void* stream);
 
@@ -137,8 +165,8 @@ int mf_crop_resize(const uint8_t* frames_in, int nf, int W, int H, int left, int
  *   mf_crop_resize_device : mf_crop_resize with the rectangle read from device memory in that
  *                           encoding; an empty / out-of-frame rectangle leaves frames_out untouched
  *                           (the host raises when it reads the rectangle back). */
-int mf_crop_combine(const int32_t* per_frame_crop, int nf, int32_t* crop_enc_out, void* stream);
-int mf_crop_resize_device(const uint8_t* frames_in, int nf, int W, int H, const int32_t* crop_enc,
+MF_API int mf_crop_combine(const int32_t* per_frame_crop, int nf, int32_t* crop_enc_out, void* stream);
+MF_API int mf_crop_resize_device(const uint8_t* frames_in, int nf, int W, int H, const int32_t* crop_enc,
                           uint8_t* frames_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -146,7 +174,17 @@ int mf_crop_resize_device(const uint8_t* frames_in, int nf, int W, int H, const 
  * DFT bins 1..5 of the frame-to-frame differences over the total energy (Parseval).
  *   s : [F, n_sys] float64;  ratio_out : [n_sys] float64 (caller averages x and y systems).
  * ---------------------------------------------------------------------------------------------- */
-int mf_stability_ratios(const double* s, int F, int64_t n_sys, double* ratio_out, void* stream);
+MF_API int mf_stability_ratios(const double* s, int F, int64_t n_sys, double* ratio_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics (used by the test-suite; not needed by a caller of the path).
+ *   mf_debug_rcp_mismatches : runs the warp kernels' correctly rounded float64 reciprocal on n seeded inputs
+ *       and returns how many differ from IEEE 1/w (expected 0); synchronises `stream`.
+ *   mf_debug_force_generic_vertex_motion : 1 = route mf_vertex_motion through the generic per-vertex path even
+ *       when the fast path applies (A/B comparisons), 0 = automatic.
+ * ---------------------------------------------------------------------------------------------- */
+MF_API long long mf_debug_rcp_mismatches(long long n, unsigned long long seed, void* scratch_u64, void* stream);
+MF_API void mf_debug_force_generic_vertex_motion(int on);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_size_t, c_void_p, c_char_p
+from ctypes import c_int, c_int64, c_longlong, c_size_t, c_ulonglong, c_void_p, c_char_p
 
 _LIB_NAME = "libmeshflow_b200.so"
 # MESHFLOW_B200_LIB lets kernel-tuning scripts point at an alternative build of the same library
@@ -40,8 +40,12 @@ _SIGNATURES = {
     "mf_warp_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
+    "mf_warp_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
     "mf_warp_crop_bounds": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
+    "mf_warp_resize_frames": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "mf_crop_resize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mf_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
@@ -49,6 +53,8 @@ _SIGNATURES = {
     "mf_crop_resize_device": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
     "mf_stability_ratios": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "mf_debug_rcp_mismatches": (c_longlong, [c_longlong, c_ulonglong, c_void_p, c_void_p]),
+    "mf_debug_force_generic_vertex_motion": (None, [c_int]),
 }
 
 _lib = None

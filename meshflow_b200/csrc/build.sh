@@ -5,7 +5,7 @@ here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${here}/../libmeshflow_b200.so"
 NVCC="${NVCC:-nvcc}"
 FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a
-       -Xcompiler -fPIC,-O2,-ffp-contract=off --expt-relaxed-constexpr ${MF_NVCC_EXTRA:-})
+       -Xcompiler -fPIC,-O2,-ffp-contract=off,-fvisibility=hidden --expt-relaxed-constexpr ${MF_NVCC_EXTRA:-})
 objs=()
 pids=()
 for f in cabi vertex_motion jacobi warp stability; do

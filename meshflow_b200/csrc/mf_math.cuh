@@ -258,7 +258,8 @@ struct alignas(16) Cell {
   double Mi[9];                 // inverse of the unstabilized -> stabilized homography, decides membership
   int lo_x, hi_x, lo_y, hi_y;   // membership bounds on the 1/32-px source coordinate (inclusive)
   int bounded;                  // 1: the support box is the bounded image of the grown rest rectangle; 0: "anywhere"
-  int pad2_;
+  unsigned edge_flags;          // kEdge*: pixels of this cell can satisfy a crop-edge search (mfs.py:1075-1098);
+                                // kMapMonotone: the remap denominator keeps its sign over the support box
 };
 
 // rest: 4 corners TL,TR,BL,BR of the rest cell (integer valued), stab: the stabilized corners already
@@ -303,7 +304,10 @@ MF_HD void cell_setup(const double* rest, const double* stab, int W, int H, Cell
   out.fhi_y = (float)(B - T) + 31.5f / 32.0f;
   out.feps = -1.0f;
   out.bounded = ((pos || neg) && finite) ? 1 : 0;
-  out.pad2_ = 0;
+  // Only cells whose rest rectangle reaches within two pixels of the frame border can produce remap
+  // coordinates that satisfy a crop-edge search (|m - e| < 1): a member pixel of cell (L..Rr, T..B) has
+  // map_x in [L-1, Rr+1], map_y in [T-1, B+1].  (kMapMonotone is added by cell_fast_setup's caller.)
+  out.edge_flags = (L <= 2 ? 1u : 0u) | (Rr >= W - 3 ? 2u : 0u) | (T <= 2 ? 4u : 0u) | (B >= H - 3 ? 8u : 0u);
   out.pad_[0] = out.pad_[1] = 0.0f;
   if ((pos || neg) && finite) {
     double fx0 = floor(x0) - 2.0, fx1 = ceil(x1) + 2.0, fy0 = floor(y0) - 2.0, fy1 = ceil(y1) + 2.0;
@@ -579,6 +583,8 @@ struct alignas(16) CellSpan {
 };
 
 static constexpr unsigned kEdgeLeft = 1u, kEdgeRight = 2u, kEdgeTop = 4u, kEdgeBottom = 8u;
+static constexpr unsigned kEdgeAny = 15u;
+static constexpr unsigned kMapMonotone = 16u;    // Cell::edge_flags only: the cell has a float32 map form (thr_u >= 0)
 static constexpr unsigned kSegNone = 0xffffu;    // no cell covers the segment: default map, border colour
 static constexpr unsigned kSegIrregular = 0xfffeu;  // resolve every pixel of this row segment exactly
 static constexpr unsigned kSegStraddle = 0xfffdu;   // lane-owner table only: a segment starts inside the group of four
@@ -879,6 +885,92 @@ MF_HD bool medium_coords(float a0, float a1, float a2, float a3, float a4, float
                       ((flags & kEdgeTop) && sy < 32 + 2) || ((flags & kEdgeBottom) && sy > 32 * (H - 2) - 2)))
     return false;
   return true;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Crop edges from row segments (mfs.py:1075-1098 without touching a pixel).
+//
+// The reference scans the float32 maps of a frame for the largest column with |map_x| < 1, the smallest
+// column with |map_x - (W-1)| < 1, the largest row with |map_y| < 1 and the smallest row with
+// |map_y - (H-1)| < 1.  A pixel's map comes from the cell that owns it, and on one output row a cell owns
+// whole intervals (row segments).  Along a row the map of one cell is (a x + b) / (h6 x + d) with a
+// denominator of constant sign (kMapMonotone), hence MONOTONE in x: the pixels inside an open band
+// (m_lo, m_hi) form one interval, whose ends follow in closed form.  Only integers within one pixel of
+// that real interval can satisfy the band: the float64 evaluation differs from real arithmetic by
+// ~1e-13 and rounding to float32 snaps any value that close to a band limit ONTO the limit (the limits
+// -1, 1, W-2, W, H-2, H are float32 numbers and rounding is monotone), where the strict comparison
+// fails either way.  Every candidate is decided by the reference's exact float64 -> float32 sequence
+// (map_row), so the result equals the scan over all pixels.  Cells without kMapMonotone are scanned.
+// ---------------------------------------------------------------------------------------------
+struct RowMapEval {
+  double h0, h2, h3, h5, h6, yh1, yh4, yh7;
+  MF_HD void init(const Cell& c, int y) {
+    const double yd = (double)y;
+    h0 = c.Hsu[0]; h2 = c.Hsu[2]; h3 = c.Hsu[3]; h5 = c.Hsu[5]; h6 = c.Hsu[6];
+    yh1 = MF_MUL(yd, c.Hsu[1]); yh4 = MF_MUL(yd, c.Hsu[4]); yh7 = MF_MUL(yd, c.Hsu[7]);
+  }
+  MF_HD float at(int x, bool use_y) const {
+    float mx, my;
+    map_row(h0, h2, h3, h5, h6, (double)x, yh1, yh4, yh7, mx, my);
+    return use_y ? my : mx;
+  }
+};
+
+// mode 0: largest x in [xa, xb] whose coordinate lies in (m_lo, m_hi); 1: smallest such x; 2: any such x.
+// Returns -1 when there is none.
+MF_HD int band_search(const RowMapEval& ev, bool use_y, float m_lo, float m_hi, int xa, int xb, int mode, bool monotone) {
+  if (xa > xb) return -1;
+  int A = xa, B = xb;
+  if (monotone) {
+    const float va = ev.at(xa, use_y), vb = ev.at(xb, use_y);
+    const bool ina = va > m_lo && va < m_hi, inb = vb > m_lo && vb < m_hi;
+    if (mode == 0) { if (inb) return xb; }
+    else { if (ina) return xa; if (mode == 2 && inb) return xb; }
+    if ((va <= m_lo && vb <= m_lo) || (va >= m_hi && vb >= m_hi)) return -1;      // monotone: nothing in between either
+    const double a = use_y ? ev.h3 : ev.h0;
+    const double b = use_y ? (ev.yh4 + ev.h5) : (ev.yh1 + ev.h2);
+    const double d = ev.yh7 + 1.0;
+    const double x1 = ((double)m_lo * d - b) / (a - (double)m_lo * ev.h6);
+    const double x2 = ((double)m_hi * d - b) / (a - (double)m_hi * ev.h6);
+    if (fabs(x1) < 1e8 && fabs(x2) < 1e8) {                                    // false for inf / NaN
+      const double lo = x1 < x2 ? x1 : x2, hi = x1 < x2 ? x2 : x1;
+      const int ca = (int)floor(lo) - 1, cb = (int)ceil(hi) + 1;
+      A = ca > xa ? ca : xa;
+      B = cb < xb ? cb : xb;
+    }
+  }
+  if (mode == 0) {
+    for (int x = B; x >= A; --x) { const float v = ev.at(x, use_y); if (v > m_lo && v < m_hi) return x; }
+  } else {
+    for (int x = A; x <= B; ++x) { const float v = ev.at(x, use_y); if (v > m_lo && v < m_hi) return x; }
+  }
+  return -1;
+}
+
+// Row segment [xa, xb] of row y owned by cell c: fold its pixels into the four edge searches.
+// e[0] = left (max), e[1] = top (max), e[2] = right (min), e[3] = bottom (min): running values, also used
+// to skip work that cannot improve them.
+MF_HD void segment_crop_edges(const Cell& c, int xa, int xb, int y, int W, int H, int* e) {
+  const unsigned fl = c.edge_flags;
+  if (!(fl & kEdgeAny) || xa > xb) return;
+  const bool mono = (fl & kMapMonotone) != 0u;
+  RowMapEval ev;
+  ev.init(c, y);
+  if (fl & kEdgeLeft) {
+    const int x = band_search(ev, false, -1.0f, 1.0f, xa > e[0] + 1 ? xa : e[0] + 1, xb, 0, mono);
+    if (x > e[0]) e[0] = x;
+  }
+  if (fl & kEdgeRight) {
+    const int x = band_search(ev, false, (float)(W - 2), (float)W, xa, xb < e[2] - 1 ? xb : e[2] - 1, 1, mono);
+    if (x >= 0 && x < e[2]) e[2] = x;
+  }
+  if ((fl & kEdgeTop) && y > e[1]) {
+    if (band_search(ev, true, -1.0f, 1.0f, xa, xb, 2, mono) >= 0) e[1] = y;
+  }
+  if ((fl & kEdgeBottom) && y < e[3]) {
+    if (band_search(ev, true, (float)(H - 2), (float)H, xa, xb, 2, mono) >= 0) e[3] = y;
+  }
 }
 
 }  // namespace mf

@@ -19,6 +19,9 @@
 //                       crop-edge searches (mfs.py:1075-1098) are warp reductions + atomics.
 //   crop_resize_kernel: cv2.resize of the cropped window back to W x H (mfs.py:1150-1155).
 //
+// warp_kernel is the GENERIC pixel kernel (float32 maps for parity tests, tiny frames); the production path --
+// row segments, analytic crop edges, the fast and the fused pixel kernels -- is in warp_fast.cuh.
+//
 // HBM layout: frames [nf][H][W][3] uint8 (row pitch 3W, no padding -- BGR24 rows are multiples of 16
 // bytes at every standard resolution); cells [nf][R*C] mf::Cell (240 B); tile lists
 // [nf][tiles][kTileCap] uint16 + counts.
@@ -47,7 +50,8 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
     int nf, int W, int H, int R, int C, int tiles_x, int tiles_y, Cell* __restrict__ cells,
     CellFast* __restrict__ fast, CellSpan* __restrict__ spans,
-    int* __restrict__ tile_count, uint16_t* __restrict__ tile_list, int32_t* __restrict__ crop_out) {
+    int* __restrict__ tile_count, uint16_t* __restrict__ tile_list, int32_t* __restrict__ crop_out,
+    int* __restrict__ edge_count, uint16_t* __restrict__ edge_tiles) {
   const int ncell = R * C;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)nf * ncell) return;
@@ -74,7 +78,6 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
   }
   Cell cell;
   cell_setup(rest, stab, W, H, cell);
-  cells[idx] = cell;
   if (fast != nullptr) {                  // fast path: box-local float32 map + membership half-planes
     CellFast cf;
     CellSpan sp;
@@ -83,13 +86,12 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
                     (int)floor(fmin(rest[1], rest[3])), (int)ceil(fmax(rest[5], rest[7])), W, H, cf, sp);
     fast[idx] = cf;
     spans[idx] = sp;
+    if (cf.thr_u >= 0.0f) cell.edge_flags |= kMapMonotone;   // the remap denominator keeps its sign over the box
   }
+  cells[idx] = cell;
   if (cell.bx0 > cell.bx1) return;
-  // Only cells whose rest rectangle reaches within two pixels of the frame border can produce remap
-  // coordinates that satisfy a crop-edge search (|m - e| < 1, mfs.py:1075-1098): a pixel mapped by
-  // cell (L..Rr, T..B) has map_x in [L-1, Rr+1], map_y in [T-1, B+1].  Tiles are tagged so that the
-  // bounds-only pass can skip everything else.
-  const bool edge_cell = rest[0] <= 2.0 || rest[1] <= 2.0 || rest[6] >= (double)(W - 3) || rest[7] >= (double)(H - 3);
+  // Tiles that hold a border cell are tagged: only their rows take part in the crop-edge searches.
+  const bool edge_cell = (cell.edge_flags & kEdgeAny) != 0u;
   const int ntiles = tiles_x * tiles_y;
   const int tx0 = cell.bx0 / kTileW, tx1 = cell.bx1 / kTileW;
   const int ty0 = cell.by0 / kTileH, ty1 = cell.by1 / kTileH;
@@ -98,7 +100,11 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
       const size_t t = (size_t)f * ntiles + (size_t)ty * tiles_x + tx;
       const int slot = atomicAdd(&tile_count[t], 1) & kCountMask;
       if (slot < kTileCap) tile_list[t * kTileCap + slot] = (uint16_t)id;
-      if (edge_cell) atomicOr(&tile_count[t], kEdgeFlag);
+      if (edge_cell) {
+        // the first border cell to tag a tile also lists it: crop_edges_kernel only visits listed tiles
+        const int old = atomicOr(&tile_count[t], kEdgeFlag);
+        if (!(old & kEdgeFlag) && edge_count != nullptr) edge_tiles[(size_t)f * ntiles + atomicAdd(&edge_count[f], 1)] = (uint16_t)(ty * tiles_x + tx);
+      }
     }
   }
 }
@@ -590,6 +596,8 @@ struct WarpWorkspace {
   uint32_t* rowseg;
   uint4* lane_owner;     // [nf][H][tiles_x] x 32 uint16: owner of each lane's group of four pixels
   uint32_t* span_tab;    // [nf][R*C][span_rows]: member interval of a cell on each row of its box
+  int* edge_count;       // [nf]: tiles of the frame that hold a border cell
+  uint16_t* edge_tiles;  // [nf][tiles]: their indices (order of arrival)
   int span_rows;
   int segcap;
 };
@@ -614,6 +622,8 @@ static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorks
   w.lane_owner = cv.take<uint4>((size_t)nf * H * tiles_x * 4);
   w.span_rows = span_rows_for(H, R);
   w.span_tab = cv.take<uint32_t>((size_t)nf * R * C * w.span_rows);
+  w.edge_count = cv.take<int>((size_t)nf);
+  w.edge_tiles = cv.take<uint16_t>((size_t)nf * tiles);
   return cv.ok();
 }
 
@@ -625,7 +635,9 @@ static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorks
 // 5-word row reads; MF_WARP_GENERIC=1 forces the generic kernel (A/B comparisons).
 static bool use_fast_path(int W, int H, int R, int C) {
   static const bool forced_generic = [] { const char* e = getenv("MF_WARP_GENERIC"); return e && e[0] == '1'; }();
-  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && (int64_t)R * C < (int64_t)mf::kSegStraddle;
+  const int64_t tiles = (int64_t)((W + mf::kTileW - 1) / mf::kTileW) * ((H + mf::kTileH - 1) / mf::kTileH);
+  return !forced_generic && W >= 16 && H >= 2 && W <= 32767 && H <= 32767 && (int64_t)R * C < (int64_t)mf::kSegStraddle &&
+         tiles <= 65535;
 }
 
 extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {
@@ -636,16 +648,25 @@ extern "C" size_t mf_warp_workspace_bytes(int nf, int W, int H, int R, int C) {
   return mf::align_up(cv.used, 256);
 }
 
-// memset + cell_setup + tile_sort: everything the pixel pass and the bounds-only pass share
+static mf::WarpTables tables_of(const mf::WarpWorkspace& w, int R, int C, int tiles_x, int tiles_y) {
+  mf::WarpTables t;
+  t.cells = w.cells; t.fast = w.fast; t.tile_count = w.tile_count; t.tile_list = w.tile_list; t.rowseg = w.rowseg;
+  t.lane_owner = (const uint16_t*)w.lane_owner; t.segcap = w.segcap; t.ncell = R * C; t.tiles_x = tiles_x; t.tiles_y = tiles_y;
+  return t;
+}
+
+// memset + cell_setup + tile_sort (+ cell_spans + row_segments on the fast path): everything that depends on the
+// vertex paths only.  On the fast path row_segments also folds the crop edges of every frame into crop_out.
 static int prepare_cells(const double* u, const double* s, const float* vertex_xy, int nf, int W, int H, int R,
                          int C, int32_t* crop_out, const mf::WarpWorkspace& w, bool fast, cudaStream_t st) {
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
   cudaError_t ce = cudaMemsetAsync(w.tile_count, 0, (size_t)nf * tiles_x * tiles_y * sizeof(int), st);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(w.edge_count, 0, (size_t)nf * sizeof(int), st);
   if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "warp: memset: %s", cudaGetErrorString(ce));
   const int64_t ncells = (int64_t)nf * R * C;
   mf::cell_setup_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(
       u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, fast ? w.fast : nullptr, fast ? w.spans : nullptr,
-      w.tile_count, w.tile_list, crop_out);
+      w.tile_count, w.tile_list, crop_out, w.edge_count, w.edge_tiles);
   if (int e = mf::check_launch("cell_setup")) return e;
   const int64_t ntiles = (int64_t)nf * tiles_x * tiles_y;
   mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
@@ -658,7 +679,13 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
     mf::row_segments_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
         w.cells, w.span_tab, w.span_rows, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.segcap, w.rowseg,
         w.lane_owner);
-    return mf::check_launch("row_segments");
+    if (int e = mf::check_launch("row_segments")) return e;
+    // one thread per (frame, listed border tile, row of the tile); frames rarely list more than a third of their tiles
+    const int64_t nedge = (int64_t)nf * tiles_x * tiles_y * mf::kTileH;
+    mf::crop_edges_kernel<<<(unsigned)((nedge + 127) / 128), 128, 0, st>>>(
+        w.cells, w.tile_count, w.tile_list, w.rowseg, w.edge_count, w.edge_tiles, nf, W, H, R * C, tiles_x, tiles_y, w.segcap,
+        crop_out);
+    return mf::check_launch("crop_edges");
   }
   return MF_OK;
 }
@@ -668,26 +695,22 @@ static dim3 fast_grid(int nf, int W, int H) {
               (unsigned)nf);
 }
 
-extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W,
-                                   int H, int R, int C, int32_t* crop_out, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-  MF_REQUIRE(u && s && vertex_xy && crop_out && workspace, "mf_warp_crop_bounds: null pointer");
+extern "C" int mf_warp_prepare(const double* u, const double* s, const float* vertex_xy, int nf, int W,
+                               int H, int R, int C, int32_t* crop_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  MF_REQUIRE(u && s && vertex_xy && crop_out && workspace, "mf_warp_prepare: null pointer");
   MF_REQUIRE(nf > 0 && nf <= 65535 && W > 1 && H > 1 && R > 0 && C > 0 && R * C <= 65535,
-             "mf_warp_crop_bounds: bad sizes");
+             "mf_warp_prepare: bad sizes");
   mf::Carver cv(workspace, workspace_bytes);
   mf::WarpWorkspace w;
   if (!mf::carve_warp(cv, nf, W, H, R, C, w))
-    return mf::fail(MF_E_WORKSPACE, "mf_warp_crop_bounds: workspace %zu < %zu bytes", workspace_bytes, cv.used);
+    return mf::fail(MF_E_WORKSPACE, "mf_warp_prepare: workspace %zu < %zu bytes", workspace_bytes, cv.used);
   cudaStream_t st = (cudaStream_t)stream;
   const bool fast = use_fast_path(W, H, R, C);
   if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, fast, st)) return e;
+  if (fast) return MF_OK;
+  // frames too small for the row-segment tables: the generic kernel evaluates the maps of the border tiles
   const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
-  if (fast) {
-    mf::warp_fast_kernel<true><<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(
-        nullptr, nullptr, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, (const uint16_t*)w.lane_owner, w.segcap,
-        crop_out, W, H, R * C, tiles_x, tiles_y, 0u);
-    return mf::check_launch("warp_fast_bounds");
-  }
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
   if ((W % mf::kTileW == 0) && (H % mf::kTileH == 0))
     mf::warp_kernel<false, true, true><<<grid, mf::kWarpThreads, 0, st>>>(
@@ -696,6 +719,12 @@ extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float
     mf::warp_kernel<false, false, true><<<grid, mf::kWarpThreads, 0, st>>>(
         nullptr, nullptr, w.cells, w.tile_count, w.tile_list, crop_out, nullptr, W, H, R * C, tiles_x, tiles_y, 0, 0, 0);
   return mf::check_launch("warp_bounds");
+}
+
+extern "C" int mf_warp_crop_bounds(const double* u, const double* s, const float* vertex_xy, int nf, int W,
+                                   int H, int R, int C, int32_t* crop_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return mf_warp_prepare(u, s, vertex_xy, nf, W, H, R, C, crop_out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const double* s,
@@ -719,9 +748,8 @@ extern "C" int mf_warp_frames(const uint8_t* frames_in, const double* u, const d
   if (int e = prepare_cells(u, s, vertex_xy, nf, W, H, R, C, crop_out, w, fast, st)) return e;
   if (fast) {
     const uint32_t border = (uint32_t)(border_b & 255) | ((uint32_t)(border_g & 255) << 8) | ((uint32_t)(border_r & 255) << 16);
-    mf::warp_fast_kernel<false><<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(
-        frames_in, frames_out, w.cells, w.fast, w.tile_count, w.tile_list, w.rowseg, (const uint16_t*)w.lane_owner, w.segcap,
-        crop_out, W, H, R * C, tiles_x, tiles_y, border);
+    mf::warp_fast_kernel<<<fast_grid(nf, W, H), mf::kWarpThreads, 0, st>>>(frames_in, frames_out,
+                                                                           tables_of(w, R, C, tiles_x, tiles_y), W, H, border);
     return mf::check_launch("warp_fast");
   }
   const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)nf);
@@ -741,12 +769,17 @@ extern "C" size_t mf_crop_resize_workspace_bytes(int W, int H) {
   return 256 + mf::align_up((size_t)W * sizeof(int4), 256) + mf::align_up((size_t)H * sizeof(int4), 256);
 }
 
+static int launch_resize_tables(int W, int H, const int32_t* enc4, void* workspace, cudaStream_t st, int4*& xtab, int4*& ytab) {
+  xtab = (int4*)((char*)workspace + 256);
+  ytab = (int4*)((char*)workspace + 256 + mf::align_up((size_t)W * sizeof(int4), 256));
+  mf::resize_table_kernel<<<(W + H + 127) / 128, 128, 0, st>>>(W, H, enc4, xtab, ytab);
+  return mf::check_launch("resize_table");
+}
+
 static int launch_crop_resize(const uint8_t* frames_in, int nf, int W, int H, const int32_t* enc4,
                               uint8_t* frames_out, void* workspace, cudaStream_t st) {
-  int4* xtab = (int4*)((char*)workspace + 256);
-  int4* ytab = (int4*)((char*)workspace + 256 + mf::align_up((size_t)W * sizeof(int4), 256));
-  mf::resize_table_kernel<<<(W + H + 127) / 128, 128, 0, st>>>(W, H, enc4, xtab, ytab);
-  if (int e = mf::check_launch("resize_table")) return e;
+  int4 *xtab, *ytab;
+  if (int e = launch_resize_tables(W, H, enc4, workspace, st, xtab, ytab)) return e;
   static const bool generic = [] { const char* e = getenv("MF_RESIZE_GENERIC"); return e && e[0] == '1'; }();
   if (generic) {
     const dim3 grid((unsigned)((W + mf::kTileW - 1) / mf::kTileW), (unsigned)((H + mf::kTileH - 1) / mf::kTileH),
@@ -797,4 +830,48 @@ extern "C" int mf_crop_resize_device(const uint8_t* frames_in, int nf, int W, in
   if (workspace_bytes < mf_crop_resize_workspace_bytes(W, H))
     return mf::fail(MF_E_WORKSPACE, "mf_crop_resize_device: workspace too small");
   return launch_crop_resize(frames_in, nf, W, H, crop_enc, frames_out, workspace, (cudaStream_t)stream);
+}
+
+// Fused pass B: warp + crop + resize of frames [first_frame, first_frame + nf) of the video whose tables
+// mf_warp_prepare left in `workspace` (carved for table_frames frames).
+extern "C" int mf_warp_resize_frames(const uint8_t* frames_in, int nf, int first_frame, int table_frames, int W, int H,
+                                     int R, int C, int border_b, int border_g, int border_r, const int32_t* crop_enc,
+                                     uint8_t* frames_out, void* workspace, size_t workspace_bytes,
+                                     void* resize_workspace, size_t resize_workspace_bytes, void* stream) {
+  MF_REQUIRE(frames_in && frames_out && crop_enc && workspace && resize_workspace, "mf_warp_resize_frames: null pointer");
+  MF_REQUIRE(nf > 0 && first_frame >= 0 && table_frames > 0 && first_frame + nf <= table_frames && table_frames <= 65535,
+             "mf_warp_resize_frames: frames [%d, %d) are not inside the %d prepared frames", first_frame, first_frame + nf,
+             table_frames);
+  MF_REQUIRE(W > 1 && H > 1 && R > 0 && C > 0 && R * C <= 65535, "mf_warp_resize_frames: bad sizes");
+  MF_REQUIRE(frames_in != frames_out, "mf_warp_resize_frames: in-place operation is not possible");
+  if (!use_fast_path(W, H, R, C))
+    return mf::fail(MF_E_UNSUPPORTED, "mf_warp_resize_frames: no row-segment tables at %dx%d with %dx%d cells "
+                                      "(use mf_warp_frames + mf_crop_resize_device)", W, H, R, C);
+  if (resize_workspace_bytes < mf_crop_resize_workspace_bytes(W, H))
+    return mf::fail(MF_E_WORKSPACE, "mf_warp_resize_frames: resize workspace too small");
+  mf::Carver cv(workspace, workspace_bytes);
+  mf::WarpWorkspace w;
+  if (!mf::carve_warp(cv, table_frames, W, H, R, C, w))
+    return mf::fail(MF_E_WORKSPACE, "mf_warp_resize_frames: workspace %zu < %zu bytes", workspace_bytes, cv.used);
+  cudaStream_t st = (cudaStream_t)stream;
+  int4 *xtab, *ytab;
+  if (int e = launch_resize_tables(W, H, crop_enc, resize_workspace, st, xtab, ytab)) return e;
+  const int tiles_x = (W + mf::kTileW - 1) / mf::kTileW, tiles_y = (H + mf::kTileH - 1) / mf::kTileH;
+  if (sizeof(mf::FusedShared) > 48 * 1024) {                 // opt-in once per device
+    static bool opted[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !opted[dev]) {
+      cudaError_t ce = cudaFuncSetAttribute(mf::warp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(mf::FusedShared));
+      if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "mf_warp_resize_frames: shared memory opt-in: %s", cudaGetErrorString(ce));
+      opted[dev] = true;
+    }
+  }
+  const uint32_t border = (uint32_t)(border_b & 255) | ((uint32_t)(border_g & 255) << 8) | ((uint32_t)(border_r & 255) << 16);
+  const dim3 grid((unsigned)((W + mf::kOutTileW - 1) / mf::kOutTileW), (unsigned)((H + mf::kOutTileH - 1) / mf::kOutTileH),
+                  (unsigned)nf);
+  mf::warp_fused_kernel<<<grid, mf::kWarpThreads, sizeof(mf::FusedShared), st>>>(
+      frames_in, frames_out, tables_of(w, R, C, tiles_x, tiles_y), first_frame, W, H, border, crop_enc, xtab, ytab);
+  return mf::check_launch("warp_fused");
 }

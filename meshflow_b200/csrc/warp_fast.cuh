@@ -1,33 +1,42 @@
-// Fast path of the mesh warp (included by warp.cu).
+// Production path of the mesh warp (included by warp.cu).
 //
-// The generic kernel (warp_kernel) decides, for every group of four pixels, which cell owns it by
-// screening candidates, and evaluates the reference's float64 remap sequence for every pixel: about
-// 190 instructions per pixel, issue-bound at 10 % of the HBM roofline.  The fast path moves every
-// decision that does not depend on pixel data out of the pixel loop:
+// Every decision that does not depend on pixel data is taken before the pixel pass, from the vertex
+// paths alone (mf_warp_prepare):
 //
 //   cell_spans_kernel   : one thread per (frame, cell, four rows of the cell's box): exact member interval of
 //                         the cell on a row (span_of_row: four half-planes + the exact test for a pixel
 //                         within rounding noise of a boundary).
 //   row_segments_kernel : one thread per (frame, row, 128-px tile): the candidates' intervals resolved by
-//                         "the last cell written wins" into <= 16 sorted segments (first x, cell id), and
-//                         the owner of each lane's group of four pixels (what the pixel kernel reads).
-//   warp_fast_kernel    : CTA = 128 x 120 output pixels, warp = 128 x 15, four adjacent pixels per thread
-//                         and row.  Per row a thread reads its group's owner (one 16-bit load, requested a
-//                         row ahead), the cell's 64-byte parameter block from L1, evaluates the remap
-//                         coordinates in float32 in box-centred form (error < eps, see mf_math.cuh) and
-//                         keeps rint() only when the value is outside the rounding band; when the four
-//                         footprints are adjacent the two source rows are read once as 4-5 aligned words
-//                         each (the next row's new line is prefetched into L1), brought to phase 0 with
-//                         funnel shifts, and the taps are regrouped with constant-selector PRMTs for the
-//                         dp2a blend.
-//                         Everything else -- pixels inside the rounding band, groups that straddle a
-//                         segment, non-adjacent footprints, taps outside the frame, crop-edge
-//                         candidates, irregular cells -- is listed in the warp's shared-memory queue and
-//                         handled by the same warp right after its rows, lanes packed: medium_pixel()
-//                         (float32 coordinate, per-pixel tap fetch) for pixels that only failed a group
-//                         condition, slow_pixel() (the reference's float64 sequence) for the rest.
+//                         "the last cell written wins" into <= 16 sorted segments (first x, cell id) and the
+//                         owner of each group of four pixels (what the pixel kernels read).
+//   crop_edges_kernel   : the frame's crop edges (mfs.py:1075-1098) from the segments of border cells by the
+//                         closed-form band search of mf_math.cuh (segment_crop_edges): the crop rectangle
+//                         of a video is known before a single pixel has been read.
 //
-// Results are identical to warp_kernel (tests/test_gpu_parity.py compares both with the oracle).
+// and two pixel kernels share one row loop (warp_rows):
+//
+//   warp_fast_kernel    : stabilized frames to global memory (the reference's stage output,
+//                         mfs.py:909-1100).  CTA = 128 x 120 output pixels, warp = 128 x 15.
+//   warp_fused_kernel   : pass B of the streamed schedule.  The crop rectangle is already known, so a CTA
+//                         produces the stabilized pixels of ONE 120 x 64 tile of the FINAL frame (+ the one
+//                         row / column of overlap cv2.resize's taps need) into shared memory and resizes
+//                         from there (mfs.py:1111-1157): the stabilized frame never exists in DRAM and the
+//                         pixels outside the crop rectangle are never computed.
+//
+// warp_rows: four adjacent pixels per thread and row.  Per row a thread reads its group's owner (one
+// 16-bit load, requested a row ahead), the cell's 64-byte parameter block from L1, evaluates the remap
+// coordinates in float32 in box-centred form (error < eps, see mf_math.cuh) and keeps rint() only when
+// the value is outside the rounding band; when the four footprints are adjacent the two source rows are
+// read once as 4-5 aligned words each (the next row's new line is prefetched into L1), brought to
+// phase 0 with funnel shifts, and the taps are regrouped with constant-selector PRMTs for the dp2a
+// blend.  Everything else -- pixels inside the rounding band, groups that straddle a segment,
+// non-adjacent footprints, taps outside the frame, irregular cells -- goes into the warp's shared-memory
+// list as ONE entry per group (slot from a ballot, so a column of straddling groups costs one store per
+// row, not a serial loop) and is handled by the same warp right after its rows, lanes packed:
+// medium_pixel() (float32 coordinate, per-pixel tap fetch) for pixels that only failed a group
+// condition, slow_pixel() (the reference's float64 sequence) for the rest.
+//
+// Results are identical to warp_kernel (tests/test_gpu_parity.py compares all of them with the oracle).
 #pragma once
 
 namespace mf {
@@ -68,6 +77,36 @@ __global__ void __launch_bounds__(128) cell_spans_kernel(const Cell* __restrict_
   }
 }
 
+// Crop edges contributed by one 128-pixel tile row (only rows of tiles that hold a border cell get here).
+__device__ __forceinline__ void row_crop_edges(const Cell* __restrict__ fcells, const uint16_t* __restrict__ list, int nraw,
+                                            int ncell, const unsigned* seg, int ns, int x0, int x1, int y, int W, int H,
+                                            int32_t* __restrict__ cr) {
+  int e[4] = {cr[0], cr[1], cr[2], cr[3]};                  // stale values are fine: they only prune
+  const int e0[4] = {e[0], e[1], e[2], e[3]};
+  if (ns < 0) {
+    // ownership of this tile row is not known per interval: every pixel the exact way
+    const bool overflow = nraw > kTileCap;
+    for (int px = x0; px <= x1; ++px) {
+      const float2 m = resolve_pixel(fcells, overflow ? nullptr : list, overflow ? ncell : nraw, px, y, (float)(W + 1), (float)(H + 1));
+      if (m.x > -1.0f && m.x < 1.0f && px > e[0]) e[0] = px;
+      if (m.y > -1.0f && m.y < 1.0f && y > e[1]) e[1] = y;
+      if (m.x > (float)(W - 2) && m.x < (float)W && px < e[2]) e[2] = px;
+      if (m.y > (float)(H - 2) && m.y < (float)H && y < e[3]) e[3] = y;
+    }
+  } else {
+    for (int i = 0; i < ns; ++i) {
+      const unsigned id = seg[i] & 0xffffu;
+      if (id == kSegNone) continue;                          // default map (W+1, H+1): never a hit
+      const int xa = (int)(seg[i] >> 16), xb = i + 1 < ns ? (int)(seg[i + 1] >> 16) - 1 : x1;
+      segment_crop_edges(fcells[id], xa, xb, y, W, H, e);
+    }
+  }
+  if (e[0] > e0[0]) atomicMax(cr + 0, e[0]);
+  if (e[1] > e0[1]) atomicMax(cr + 1, e[1]);
+  if (e[2] < e0[2]) atomicMin(cr + 2, e[2]);
+  if (e[3] < e0[3]) atomicMin(cr + 3, e[3]);
+}
+
 __global__ void __launch_bounds__(128) row_segments_kernel(
     const Cell* __restrict__ cells, const uint32_t* __restrict__ span_tab, int span_rows, const int* __restrict__ tile_count,
     const uint16_t* __restrict__ tile_list, int nf, int W, int H, int ncell, int tiles_x, int tiles_y, int segcap,
@@ -80,7 +119,8 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   const int y = (int)(fy % H), f = (int)(fy / H);
   const int x0 = tx * kTileW, x1 = min(W - 1, x0 + kTileW - 1);
   const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(y / kTileH) * tiles_x + tx;
-  const int nraw = __ldg(tile_count + tile) & kCountMask;
+  const int craw = __ldg(tile_count + tile);
+  const int nraw = craw & kCountMask;
   uint32_t* out = rowseg + (size_t)idx * segcap;
   SegBuilder sb;
   sb.begin(x0, x1);
@@ -146,23 +186,80 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   uint4* lo = lane_owner + (size_t)idx * 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) lo[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+
 }
 
-// Tap fetch + blend + 3-byte store of one pixel from its 1/32-px source coordinate.
-__device__ __forceinline__ void remap_store_pixel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst_frame, int px,
-                                                  int py, int W, int H, int ix, int iy, int ax, int ay, uint32_t border) {
-  uint32_t o;
-  if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) {
-    o = blend_interior(src, W * 3, ix, iy, ax, ay);
-  } else if (ix < -1 || ix >= W || iy < -1 || iy >= H) {
-    o = border;
-  } else {
-    uint8_t t3[3];
-    remap_pixel(src, W, H, ix, iy, ax, ay, (int)(border & 0xffu), (int)((border >> 8) & 0xffu), (int)((border >> 16) & 0xffu), t3);
-    o = (uint32_t)t3[0] | ((uint32_t)t3[1] << 8) | ((uint32_t)t3[2] << 16);
+// Crop edges of every frame (mfs.py:1075-1098) from the row segments of the tiles that hold a border cell (listed
+// per frame by cell_setup_kernel): one thread per (frame, listed tile, row of the tile).  A kernel of its own so
+// that the float64 registers of the band search do not burden the segment builder.
+__global__ void __launch_bounds__(128) crop_edges_kernel(
+    const Cell* __restrict__ cells, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
+    const uint32_t* __restrict__ rowseg, const int* __restrict__ edge_count, const uint16_t* __restrict__ edge_tiles, int nf,
+    int W, int H, int ncell, int tiles_x, int tiles_y, int segcap, int32_t* __restrict__ crop_out) {
+  const int ntiles = tiles_x * tiles_y;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nf * ntiles * kTileH) return;
+  const int ry = (int)(idx % kTileH);
+  const int64_t fs = idx / kTileH;
+  const int slot = (int)(fs % ntiles), f = (int)(fs / ntiles);
+  if (slot >= __ldg(edge_count + f)) return;                // listed tiles come first: whole warps leave here
+  const int t = (int)__ldg(edge_tiles + (size_t)f * ntiles + slot);
+  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const int y = ty * kTileH + ry;
+  if (y >= H) return;
+  const size_t tile = (size_t)f * ntiles + t;
+  const int craw = __ldg(tile_count + tile);
+  const int x0 = tx * kTileW, x1 = min(W - 1, x0 + kTileW - 1);
+  const uint32_t* rs = rowseg + (((size_t)f * H + y) * tiles_x + tx) * segcap;
+  unsigned seg[kSegMax];
+  int ns = 0;
+  for (int i = 0; i < segcap; ++i) {
+    const unsigned v = __ldg(rs + i);
+    if (v == kSegSentinel) break;
+    seg[ns++] = v;
   }
-  uint8_t* d = dst_frame + ((size_t)py * W + px) * 3;
+  if ((seg[0] & 0xffffu) == kSegIrregular) ns = -1;
+  row_crop_edges(cells + (size_t)f * ncell, tile_list + tile * kTileCap, craw & kCountMask, ncell, seg, ns, x0, x1, y, W, H,
+                 crop_out + 4 * f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pixel pass
+// ---------------------------------------------------------------------------------------------------------------
+struct WarpTables {
+  const Cell* cells;          // [frames][ncell]
+  const CellFast* fast;
+  const int* tile_count;
+  const uint16_t* tile_list;
+  const uint32_t* rowseg;
+  const uint16_t* lane_owner;
+  int segcap, ncell, tiles_x, tiles_y;
+};
+
+// Where a pixel kernel puts its stabilized pixels: global memory (row pitch 3 W) or the CTA's shared-memory tile.
+// `base` addresses pixel (ox, oy); both kinds are reached through generic stores on the rare paths, the hot path
+// uses st.shared / st.global.cs directly.
+struct PixelSink {
+  uint8_t* base;
+  unsigned pitch;
+  int ox, oy;
+  __device__ __forceinline__ uint8_t* at(int px, int py) const {
+    return base + (size_t)(py - oy) * pitch + (size_t)(px - ox) * 3;
+  }
+};
+
+__device__ __forceinline__ void put_pixel(uint8_t* d, uint32_t o) {
   d[0] = (uint8_t)(o & 0xffu); d[1] = (uint8_t)((o >> 8) & 0xffu); d[2] = (uint8_t)((o >> 16) & 0xffu);
+}
+
+// Tap fetch + blend of one pixel from its 1/32-px source coordinate; returns BGRx.
+__device__ __forceinline__ uint32_t remap_one(const uint8_t* __restrict__ src, int W, int H, int ix, int iy, int ax, int ay,
+                                              uint32_t border) {
+  if ((unsigned)ix < (unsigned)(W - 3) && (unsigned)iy < (unsigned)(H - 1)) return blend_interior(src, W * 3, ix, iy, ax, ay);
+  if (ix < -1 || ix >= W || iy < -1 || iy >= H) return border;
+  uint8_t t3[3];
+  remap_pixel(src, W, H, ix, iy, ax, ay, (int)(border & 0xffu), (int)((border >> 8) & 0xffu), (int)((border >> 16) & 0xffu), t3);
+  return (uint32_t)t3[0] | ((uint32_t)t3[1] << 8) | ((uint32_t)t3[2] << 16);
 }
 
 // Owner of one pixel from its row's segment list.
@@ -179,17 +276,13 @@ __device__ __forceinline__ unsigned pixel_owner(const uint32_t* __restrict__ rs,
 // One pixel that only failed a GROUP condition (the group straddles two cells, footprints not
 // adjacent, taps near the frame border): the float32 coordinate of the pixel's own cell is still exact
 // outside the rounding band, only the tap fetch is per pixel.  Returns false -- nothing written -- when
-// the pixel needs the float64 sequence after all (inside the band, crop-edge candidate, cell without
-// float32 form, irregular segment).
-__device__ __forceinline__ bool medium_pixel(int px, int py, unsigned id, const uint8_t* __restrict__ src,
-                                             uint8_t* __restrict__ dst_frame, const CellFast* __restrict__ ffast, int W,
-                                             int H, uint32_t border) {
+// the pixel needs the float64 sequence after all (inside the band, cell without float32 form, irregular
+// segment).
+__device__ __forceinline__ bool medium_pixel(int px, int py, unsigned id, const uint8_t* __restrict__ src, uint8_t* dst,
+                                             const CellFast* __restrict__ ffast, int W, int H, uint32_t border) {
   if (id == kSegIrregular) return false;
-  if (id == kSegNone) {                                      // default map (W+1, H+1): border colour, no crop hit
-    if (dst_frame != nullptr) {
-      uint8_t* d = dst_frame + ((size_t)py * W + px) * 3;
-      d[0] = (uint8_t)(border & 0xffu); d[1] = (uint8_t)((border >> 8) & 0xffu); d[2] = (uint8_t)((border >> 16) & 0xffu);
-    }
+  if (id == kSegNone) {                                      // default map (W+1, H+1): border colour
+    put_pixel(dst, border);
     return true;
   }
   const float4* cp = reinterpret_cast<const float4*>(ffast + id);
@@ -197,29 +290,26 @@ __device__ __forceinline__ bool medium_pixel(int px, int py, unsigned id, const 
   const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
   int sx, sy;
   if (!medium_coords(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, __int_as_float(q3.w), __float_as_int(q2.z),
-                     __float_as_int(q2.w), q3.x, q3.y, (unsigned)q3.z, px, py, W, H, sx, sy))
+                     __float_as_int(q2.w), q3.x, q3.y, 0u, px, py, W, H, sx, sy))
     return false;
-  if (dst_frame != nullptr) remap_store_pixel(src, dst_frame, px, py, W, H, sx >> 5, sy >> 5, sx & 31, sy & 31, border);
+  put_pixel(dst, remap_one(src, W, H, sx >> 5, sy >> 5, sx & 31, sy & 31, border));
   return true;
 }
 
 // One pixel the exact way: owner from the segment list (or the per-pixel search for irregular segments),
-// the reference's float64 remap sequence, the four crop-edge searches, the general tap fetch.
-__device__ __noinline__ void slow_pixel(int px, int py, int f, const uint8_t* __restrict__ src,
-                                        uint8_t* __restrict__ dst_frame, const Cell* __restrict__ fcells,
-                                        const int* __restrict__ tile_count,
-                                        const uint16_t* __restrict__ tile_list, const uint32_t* __restrict__ rowseg,
-                                        int segcap, int32_t* __restrict__ crop_out, int W, int H, int ncell, int tiles_x,
-                                        int tiles_y, uint32_t border) {
+// the reference's float64 remap sequence, the general tap fetch.
+__device__ __noinline__ void slow_pixel(int px, int py, int f, const uint8_t* __restrict__ src, uint8_t* dst,
+                                        const WarpTables T, int W, int H, uint32_t border) {
   const int tx = px / kTileW;
-  const uint32_t* rs = rowseg + (((size_t)f * H + py) * tiles_x + tx) * segcap;
-  const unsigned id = pixel_owner(rs, segcap, px);
+  const uint32_t* rs = T.rowseg + (((size_t)f * H + py) * T.tiles_x + tx) * T.segcap;
+  const Cell* fcells = T.cells + (size_t)f * T.ncell;
+  const unsigned id = pixel_owner(rs, T.segcap, px);
   float mx = (float)(W + 1), my = (float)(H + 1);           // mfs.py:983-984
   if (id == kSegIrregular) {
-    const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
-    const int nraw = __ldg(tile_count + tile) & kCountMask;
+    const size_t tile = (size_t)f * T.tiles_x * T.tiles_y + (size_t)(py / kTileH) * T.tiles_x + tx;
+    const int nraw = __ldg(T.tile_count + tile) & kCountMask;
     const bool overflow = nraw > kTileCap;
-    const float2 m = resolve_pixel(fcells, overflow ? nullptr : tile_list + tile * kTileCap, overflow ? ncell : nraw,
+    const float2 m = resolve_pixel(fcells, overflow ? nullptr : T.tile_list + tile * kTileCap, overflow ? T.ncell : nraw,
                                    px, py, mx, my);
     mx = m.x; my = m.y;
   } else if (id != kSegNone) {
@@ -228,15 +318,9 @@ __device__ __noinline__ void slow_pixel(int px, int py, int f, const uint8_t* __
     const double y = (double)py;
     map_row(h01.x, h23.x, h23.y, h45.y, h67.x, (double)px, MF_MUL(y, h01.y), MF_MUL(y, h45.x), MF_MUL(y, h67.y), mx, my);
   }
-  int32_t* cr = crop_out + 4 * f;                           // mfs.py:1075-1098; plain read first: most hits do not improve
-  if (mx > -1.0f && mx < 1.0f && px > cr[0]) atomicMax(cr + 0, px);
-  if (my > -1.0f && my < 1.0f && py > cr[1]) atomicMax(cr + 1, py);
-  if (mx > (float)(W - 2) && mx < (float)W && px < cr[2]) atomicMin(cr + 2, px);
-  if (my > (float)(H - 2) && my < (float)H && py < cr[3]) atomicMin(cr + 3, py);
-  if (dst_frame == nullptr) return;
   int ix, iy, ax, ay;
   remap_coords(mx, my, ix, iy, ax, ay);
-  remap_store_pixel(src, dst_frame, px, py, W, H, ix, iy, ax, ay, border);
+  put_pixel(dst, remap_one(src, W, H, ix, iy, ax, ay, border));
 }
 
 // (B, G) pairs and R pair of pixel J of a group from the phase-0 words s0..s3 of one source row:
@@ -263,85 +347,125 @@ __device__ __forceinline__ void blend_group_pixel(const uint32_t (&st)[4], const
   vr = __dp2a_lo(wb, br, __dp2a_lo(wa, tr, 512u)) >> 10;
 }
 
-#ifndef MF_FAST_MINBLOCKS
-#define MF_FAST_MINBLOCKS 4
-#endif
-template <bool kBoundsOnly>
-__global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_kernel(
-    const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, const Cell* __restrict__ cells,
-    const CellFast* __restrict__ fast, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
-    const uint32_t* __restrict__ rowseg, const uint16_t* __restrict__ lane_owner, int segcap,
-    int32_t* __restrict__ crop_out, int W, int H, int ncell, int tiles_x, int tiles_y, uint32_t border) {
-  __shared__ uint16_t warp_queue[kWarpThreads / 32][kTileW * kFastRows];   // every pixel of a warp fits
-  const int f = blockIdx.z, tx = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int px0 = tx * kTileW + lane * kPix;
-  const int y_first = blockIdx.y * kFastTileH + warp * kFastRows;
-  const int npx = min(kPix, W - px0);                        // <= 0: this lane has no pixels
-  const uint8_t* src = frames_in + (size_t)f * H * W * 3;
-  uint8_t* dstf = kBoundsOnly ? nullptr : frames_out + (size_t)f * H * W * 3;
-  const unsigned fcell0 = (unsigned)f * (unsigned)ncell;     // < 2^32: at most 65535 frames x 65533 cells
-  const unsigned pitch = (unsigned)W * 3u;
-  const bool word_store = ((pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(dstf) & 3u) == 0u);
-  // running pointers: one add per row instead of a 64-bit multiply chain
-  const size_t own_stride = (size_t)tiles_x * 32;
-  const uint16_t* own = lane_owner + (((size_t)f * H + y_first) * tiles_x + tx) * 32 + lane;
-  uint8_t* drow = kBoundsOnly ? nullptr : dstf + ((size_t)y_first * W + px0) * 3;
+// Float32 remap coordinates of a group of four adjacent pixels through one cell: nu / nv = rint(U), rint(V) +
+// kRoundMagicBits as raw bits, du / dv = distance of U, V from that integer.  Returns true when all four pixels
+// are outside the rounding band (NaN -- a cell without float32 form -- compares false).
+__device__ __forceinline__ bool group_coords(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+                                             float a8, float thr_u, float thr_v, int cbx0, int cby0, int px0, int py,
+                                             unsigned (&nu)[kPix], unsigned (&nv)[kPix], float (&du)[kPix], float (&dv)[kPix]) {
+  const float fy = (float)(py - cby0);
+  const float bx = fmaf(a1, fy, a2), by = fmaf(a4, fy, a5), bw = fmaf(a7, fy, a8);
+  const float fx = (float)(px0 - cbx0);
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    const float x = fx + (float)j;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(a6, x, bw)));
+    const float U = __fmul_rn(fmaf(a0, x, bx), r), V = __fmul_rn(fmaf(a3, x, by), r);
+    const float tU = __fadd_rn(U, kRoundMagic), tV = __fadd_rn(V, kRoundMagic);
+    du[j] = __fsub_rn(U, __fsub_rn(tU, kRoundMagic));
+    dv[j] = __fsub_rn(V, __fsub_rn(tV, kRoundMagic));
+    nu[j] = __float_as_uint(tU); nv[j] = __float_as_uint(tV);
+  }
+  const float wu = fmaxf(fmaxf(fabsf(du[0]), fabsf(du[1])), fmaxf(fabsf(du[2]), fabsf(du[3])));
+  const float wv = fmaxf(fmaxf(fabsf(dv[0]), fabsf(dv[1])), fmaxf(fabsf(dv[2]), fabsf(dv[3])));
+  // fmaxf drops a NaN operand, but a cell either has finite coefficients (no NaN at all) or none (four NaNs)
+  return wu <= thr_u && wv <= thr_v;
+}
 
-  // four bits per row, newest row in the low bits: pixel j of the row takes the float64 path / the per-pixel tap fetch
-  unsigned long long exmask = 0ull, medmask = 0ull;
-  int rows_done = 0;
+// List entry of one group of four pixels: lane (5 bits) | row within the warp's rows (5 bits) | pixel mask (4 bits).
+// Two lists per warp: groups with pixels for the per-pixel tap fetch, groups with pixels for the float64 path.
+static constexpr int kSlowList = 192;                       // pixels gathered for one float64 batch (>= 128 + 32 + 32)
+
+template <int kRows>
+struct WarpScratch {
+  uint16_t med[32 * kRows];                                  // every group of a warp's kRows rows fits
+  uint16_t ex[32 * kRows + 32];                              // + one late entry per lane (see warp_rows)
+  uint16_t slow[kSlowList];
+};
+
+// The rows [y_first, y_first + nrows) x the 128 columns [X0, X0 + 128) of frame f, restricted to the columns
+// [x_lo, x_hi] the caller needs (multiples of four are NOT required; groups that do not touch the range are
+// skipped).  kShared: `sink` is the CTA's shared-memory tile (sink_shared = its shared-window address).
+template <bool kShared>
+__device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const WarpTables& T, int f, int W, int H, int X0,
+                                          int y_first, int nrows, int x_lo, int x_hi, const PixelSink& sink,
+                                          unsigned sink_shared, uint32_t border, uint16_t* __restrict__ q_med,
+                                          uint16_t* __restrict__ q_ex, uint16_t* __restrict__ q_slow, int lane) {
+  const int px0 = X0 + lane * kPix;
+  int npx = min(kPix, W - px0);                              // <= 0: this lane has no pixels
+  if (px0 > x_hi || px0 + kPix - 1 < x_lo) npx = 0;
+  const unsigned fcell0 = (unsigned)f * (unsigned)T.ncell;   // < 2^32: at most 65535 frames x 65533 cells
+  const unsigned pitch = (unsigned)W * 3u;
+  const bool word_store = kShared || (((sink.pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(sink.at(px0, y_first)) & 3u) == 0u));
+  // running pointers: one add per row instead of a 64-bit multiply chain
+  const size_t own_stride = (size_t)T.tiles_x * 32;
+  const uint16_t* own = T.lane_owner + ((size_t)f * H + y_first) * own_stride + (px0 >> 2);
+  uint8_t* drow = kShared ? nullptr : sink.at(px0, y_first);
+  unsigned srow = kShared ? sink_shared + (unsigned)(y_first - sink.oy) * sink.pitch + (unsigned)(px0 - sink.ox) * 3u : 0u;
+  const CellFast* ffast = T.fast + fcell0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int n_med = 0, n_ex = 0;                                   // entries in the warp's two lists (warp-uniform)
 
   // the owner of the next row's group is requested one row ahead (it comes from L2)
   unsigned own_next = kSegNone;
-  if (y_first < H && npx > 0) own_next = __ldg(own);
+  if (nrows > 0 && npx > 0) own_next = __ldg(own);
 #pragma unroll 1
-  for (int r = 0; r < kFastRows; ++r, own += own_stride, drow += pitch) {
+  for (int r = 0; r < nrows; ++r, own += own_stride, drow += kShared ? 0 : sink.pitch, srow += kShared ? sink.pitch : 0u) {
     const int py = y_first + r;
-    if (py >= H) break;
-    ++rows_done;
-    exmask <<= 4; medmask <<= 4;
-    if (npx <= 0) continue;
     const unsigned id = own_next;
-    if (r + 1 < kFastRows && py + 1 < H) own_next = __ldg(own + own_stride);
-    if (kBoundsOnly) {                                       // only tiles that hold a border cell can produce a hit
-      const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(py / kTileH) * tiles_x + tx;
-      if (!(__ldg(tile_count + tile) & kEdgeFlag)) continue;
-    }
-    unsigned push = 0u, med = 0u;                            // bit j: pixel j -> float64 path / per-pixel tap fetch
+    if (r + 1 < nrows && npx > 0) own_next = __ldg(own + own_stride);
+    unsigned flag = 0u;                                      // bits 0-3: per-pixel tap fetch, bits 4-7: float64 path
     bool fast_group = false;
     unsigned nu[kPix], nv[kPix];
-    int ix0 = 0, iy0 = 0, base_x = 0, base_y = 0;
-    if (id >= kSegStraddle || npx < kPix) {                  // one test on the hot path; the rare owners sort themselves out here
-      if (id == kSegIrregular) {
-        push = (1u << npx) - 1u;
-      } else if (id != kSegNone || npx < kPix) {
-        med = (1u << npx) - 1u;
-      } else if (!kBoundsOnly) {                             // no cell: map (W+1, H+1), border colour, no crop hit
-        uint32_t o[kPix] = {border, border, border, border};
-        store_bgr4(drow, o, kPix, word_store);
+    int ix0 = 0, iy0 = 0;
+    if (npx > 0) {
+      if (id >= kSegStraddle || npx < kPix) {                // one test on the hot path; the rare owners sort themselves out here
+        const unsigned all = (1u << npx) - 1u;
+        if (id == kSegIrregular) {
+          flag = all << 4;
+        } else if (id != kSegNone || npx < kPix) {
+          flag = all;
+        } else {                                             // no cell: map (W+1, H+1), border colour
+          const uint32_t w0 = border | (border << 24), w1 = (border >> 8) | (border << 16), w2 = (border >> 16) | (border << 8);
+          if (kShared) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(srow), "r"(w0));
+            asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(srow), "r"(w1));
+            asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(srow), "r"(w2));
+          } else {
+            uint32_t o[kPix] = {border, border, border, border};
+            store_bgr4(drow, o, kPix, word_store);
+          }
+        }
+      } else {
+        // the cell's parameters come from L1 every row: cheaper than keeping 16 registers alive across the gather
+        const float4* cp = reinterpret_cast<const float4*>(ffast + id);
+        const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
+        const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
+        const float thr_u = q2.y, thr_v = __int_as_float(q3.w);
+        float du[kPix], dv[kPix];
+        const bool all_safe = group_coords(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, thr_u, thr_v,
+                                           __float_as_int(q2.z), __float_as_int(q2.w), px0, py, nu, nv, du, dv);
+        const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
+        const unsigned spread = (nu[1] - bu - 32u) | (nu[2] - bu - 64u) | (nu[3] - bu - 96u) | (nv[1] - bv) | (nv[2] - bv) |
+                                (nv[3] - bv);
+        ix0 = (int)(bu - kRoundMagicBits + (unsigned)q3.x) >> 5;
+        iy0 = (int)(bv - kRoundMagicBits + (unsigned)q3.y) >> 5;
+        // adjacent footprints (pixel j reads source columns ix0+j, ix0+j+1 of rows iy0, iy0+1) with every tap -- and
+        // the 5-word row reads -- inside the frame
+        fast_group = spread < 32u && (unsigned)ix0 <= (unsigned)(W - 8) && (unsigned)iy0 <= (unsigned)(H - 2);
+        if (!all_safe) {                                     // rare: which of the four are inside the rounding band
+          unsigned bad = 0u;
+#pragma unroll
+          for (int j = 0; j < kPix; ++j)
+            if (!(fabsf(du[j]) <= thr_u && fabsf(dv[j]) <= thr_v)) bad |= 1u << j;
+          flag = bad << 4;
+          if (!(thr_u >= 0.0f)) { flag = 15u << 4; fast_group = false; }     // cell without float32 form
+        }
+        if (!fast_group) flag |= 15u & ~(flag >> 4);         // only the group shape failed: per-pixel tap fetch
       }
-    } else {
-      // the cell's parameters come from L1 every row: cheaper than keeping 16 registers alive across the gather
-      const float4* cp = reinterpret_cast<const float4*>(fast + (size_t)(fcell0 + id));
-      const float4 q0 = __ldg(cp), q1 = __ldg(cp + 1), q2 = __ldg(cp + 2);
-      const int4 q3 = __ldg(reinterpret_cast<const int4*>(cp + 3));
-      const float a0 = q0.x, a1 = q0.y, a2 = q0.z, a3 = q0.w, a4 = q1.x, a5 = q1.y, a6 = q1.z, a7 = q1.w, a8 = q2.x, thr = q2.y;
-      const int cbx0 = __float_as_int(q2.z), cby0 = __float_as_int(q2.w);
-      base_x = q3.x; base_y = q3.y;
-      const unsigned flags = (unsigned)q3.z;
-      const float thr_v = __int_as_float(q3.w);
-      // no early exit for cells without float32 form (thr < 0: their coefficients are zero, every pixel comes out
-      // "in the band"): a branch here would serialise the four parameter loads behind the first one
-      const unsigned bad = fast_group_coords(a0, a1, a2, a3, a4, a5, a6, a7, a8, thr, thr_v, cbx0, cby0, px0, py, nu, nv);
-      bool edge;
-      push = fast_group_plan(nu, nv, bad, base_x, base_y, flags, W, H, kBoundsOnly, ix0, iy0, fast_group, edge);
-      if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }   // only the group shape failed
-      if (thr < 0.0f) { push = 15u; med = 0u; fast_group = false; }
     }
-    exmask |= push;
-    medmask |= med;
-    if (!kBoundsOnly && fast_group) {
+    if (fast_group) {
       const unsigned bu = nu[0] & ~31u, bv = nv[0] & ~31u;
       const uintptr_t p0 = reinterpret_cast<uintptr_t>(src) + (unsigned)iy0 * pitch + (unsigned)ix0 * 3u;
       const uintptr_t p1 = p0 + pitch;
@@ -368,68 +492,273 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
       blend_group_pixel<1>(st, sb, nu[1] - bu - 32u, nv[1] - bv, vb[1], vg[1], vr[1]);
       blend_group_pixel<2>(st, sb, nu[2] - bu - 64u, nv[2] - bv, vb[2], vg[2], vr[2]);
       blend_group_pixel<3>(st, sb, nu[3] - bu - 96u, nv[3] - bv, vb[3], vg[3], vr[3]);
-      if (word_store) {
+      const uint32_t o0 = __byte_perm(__byte_perm(vb[0], vg[0], 0x0040), __byte_perm(vr[0], vb[1], 0x0040), 0x5410);
+      const uint32_t o1 = __byte_perm(__byte_perm(vg[1], vr[1], 0x0040), __byte_perm(vb[2], vg[2], 0x0040), 0x5410);
+      const uint32_t o2 = __byte_perm(__byte_perm(vr[2], vb[3], 0x0040), __byte_perm(vg[3], vr[3], 0x0040), 0x5410);
+      if (kShared) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(srow), "r"(o0));
+        asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(srow), "r"(o1));
+        asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(srow), "r"(o2));
+      } else if (word_store) {
         uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
-        __stcs(d32 + 0, __byte_perm(__byte_perm(vb[0], vg[0], 0x0040), __byte_perm(vr[0], vb[1], 0x0040), 0x5410));
-        __stcs(d32 + 1, __byte_perm(__byte_perm(vg[1], vr[1], 0x0040), __byte_perm(vb[2], vg[2], 0x0040), 0x5410));
-        __stcs(d32 + 2, __byte_perm(__byte_perm(vr[2], vb[3], 0x0040), __byte_perm(vg[3], vr[3], 0x0040), 0x5410));
+        __stcs(d32 + 0, o0); __stcs(d32 + 1, o1); __stcs(d32 + 2, o2);
       } else {
 #pragma unroll
         for (int j = 0; j < kPix; ++j) { drow[3 * j] = (uint8_t)vb[j]; drow[3 * j + 1] = (uint8_t)vg[j]; drow[3 * j + 2] = (uint8_t)vr[j]; }
       }
     }
-  }
-  // ---- what the fast path declined, handled by this warp right away (its source rows are still in L1 / L2):
-  //      one scan for both masks (counts packed as 16-bit halves), entries in the warp's shared-memory list ----
-  const int mine = __popcll(medmask) | (__popcll(exmask) << 16);
-  int incl = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  const int totals = __shfl_sync(0xffffffffu, incl, 31);
-  if (totals == 0) return;
-  const int n_med = totals & 0xffff, n_ex = totals >> 16;
-  uint16_t* wq = warp_queue[warp];                          // [0, n_med): per-pixel tap fetch; [n_med, n_med + n_ex): float64
-  {
-    int slot = (incl & 0xffff) - (mine & 0xffff);
-    while (medmask != 0ull) {
-      const int b = __ffsll((long long)medmask) - 1;
-      medmask &= medmask - 1ull;
-      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((rows_done - 1 - (b >> 2)) << 7));
-    }
-    slot = n_med + (incl >> 16) - (mine >> 16);
-    while (exmask != 0ull) {
-      const int b = __ffsll((long long)exmask) - 1;
-      exmask &= exmask - 1ull;
-      wq[slot++] = (uint16_t)((lane * kPix + (b & 3)) | ((rows_done - 1 - (b >> 2)) << 7));
+    // one list entry per group that declined (or partly declined) the fast path: slots from ballots
+    if (__any_sync(0xffffffffu, flag != 0u)) {
+      const unsigned mm = flag & 15u, xm = flag >> 4;
+      const unsigned bal_m = __ballot_sync(0xffffffffu, mm != 0u), bal_x = __ballot_sync(0xffffffffu, xm != 0u);
+      const unsigned tag = (unsigned)lane | ((unsigned)r << 5);
+      if (mm != 0u) q_med[n_med + __popc(bal_m & lt_mask)] = (uint16_t)(tag | (mm << 10));
+      if (xm != 0u) q_ex[n_ex + __popc(bal_x & lt_mask)] = (uint16_t)(tag | (xm << 10));
+      n_med += __popc(bal_m);
+      n_ex += __popc(bal_x);
     }
   }
+  if ((n_med | n_ex) == 0) return;
   __syncwarp();
-  const CellFast* ffast2 = fast + (size_t)f * ncell;
-  int n_failed = 0;                                          // pixels whose tap fetch declined, compacted to the list's front
-  for (int i0 = 0; i0 < n_med; i0 += 32) {
-    const int i = i0 + lane;
+  // ---- what the fast path declined, handled by this warp right away (its source rows are still in L1 / L2) ----
+  // (1) per-pixel tap fetch: eight groups x four pixels per step.  A pixel that turns out to be inside the rounding
+  //     band after all (rare) is remembered by its lane and joins the float64 list as a one-pixel group at the end;
+  //     a lane that already remembers one has the warp work the remembered pixels off first.
+  const int sub = lane >> 2, j = lane & 3;
+  unsigned pend = 0u;                                        // remembered entry (mask != 0) or 0
+  for (int i0 = 0; i0 < n_med; i0 += 8) {
+    const int i = i0 + sub;
     bool failed = false;
     unsigned e = 0u;
     if (i < n_med) {
-      e = wq[i];
-      const int qx = tx * kTileW + (int)(e & 127u), qy = y_first + (int)(e >> 7);
-      const uint32_t* rsq = rowseg + (((size_t)f * H + qy) * tiles_x + tx) * segcap;
-      failed = !medium_pixel(qx, qy, pixel_owner(rsq, segcap, qx), src, dstf, ffast2, W, H, border);
+      e = q_med[i];
+      if ((e >> (10 + j)) & 1u) {
+        const int qx = X0 + (int)(e & 31u) * kPix + j, qy = y_first + (int)((e >> 5) & 31u);
+        const uint32_t* rsq = T.rowseg + (((size_t)f * H + qy) * T.tiles_x + qx / kTileW) * T.segcap;
+        failed = !medium_pixel(qx, qy, pixel_owner(rsq, T.segcap, qx), src, sink.at(qx, qy), ffast, W, H, border);
+      }
     }
-    const unsigned fb = __ballot_sync(0xffffffffu, failed);  // rare: the pixel is in the rounding band after all
-    __syncwarp();                                            // every lane has read its entry: the front may be reused
-    if (failed) wq[n_failed + __popc(fb & ((1u << lane) - 1u))] = (uint16_t)e;
-    n_failed += __popc(fb);
+    if (__any_sync(0xffffffffu, failed)) {
+      if (__any_sync(0xffffffffu, failed && pend != 0u)) {
+        if (pend != 0u) {
+          const int qx = X0 + (int)(pend & 31u) * kPix + (__ffs((int)(pend >> 10)) - 1), qy = y_first + (int)((pend >> 5) & 31u);
+          slow_pixel(qx, qy, f, src, sink.at(qx, qy), T, W, H, border);
+        }
+        pend = 0u;
+      }
+      if (failed) pend = (e & 1023u) | (1u << (10 + j));
+    }
+  }
+  {
+    const unsigned pb = __ballot_sync(0xffffffffu, pend != 0u);
+    if (pend != 0u) q_ex[n_ex + __popc(pb & lt_mask)] = (uint16_t)pend;
+    n_ex += __popc(pb);
   }
   __syncwarp();
-  const Cell* fcells = cells + (size_t)f * ncell;
-  for (int i = lane; i < n_failed + n_ex; i += 32) {
-    const unsigned e = wq[i < n_failed ? i : n_med + (i - n_failed)];
-    slow_pixel(tx * kTileW + (int)(e & 127u), y_first + (int)(e >> 7), f, src, dstf, fcells, tile_count, tile_list, rowseg,
-               segcap, crop_out, W, H, ncell, tiles_x, tiles_y, border);
+  // (2) float64 path: the groups' flagged pixels are compacted into a pixel list, 32 groups at a time, and the list
+  //     is worked off whenever it cannot take another batch
+  int ns = 0;                                                // pixels waiting in q_slow (warp-uniform)
+  for (int i0 = 0; i0 < n_ex; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned e = i < n_ex ? q_ex[i] : 0u;
+    unsigned m = (e >> 10) & 15u;
+    const int cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int slot = ns + incl - cnt;
+    while (m != 0u) {
+      const int b = __ffs((int)m) - 1;
+      m &= m - 1u;
+      q_slow[slot++] = (uint16_t)(((e & 31u) * kPix + (unsigned)b) | (((e >> 5) & 31u) << 7));
+    }
+    ns += total;
+    __syncwarp();
+    if (ns > kSlowList - 128 || i0 + 32 >= n_ex) {
+      for (int k = lane; k < ns; k += 32) {
+        const unsigned p = q_slow[k];
+        const int qx = X0 + (int)(p & 127u), qy = y_first + (int)(p >> 7);
+        slow_pixel(qx, qy, f, src, sink.at(qx, qy), T, W, H, border);
+      }
+      ns = 0;
+      __syncwarp();
+    }
+  }
+}
+
+#ifndef MF_FAST_MINBLOCKS
+#define MF_FAST_MINBLOCKS 4
+#endif
+// Stabilized frames to global memory.  CTA = 128 x kFastTileH output pixels, warp = 128 x kFastRows.
+__global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_kernel(
+    const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, const WarpTables T, int W, int H, uint32_t border) {
+  __shared__ WarpScratch<kFastRows> scratch[kWarpThreads / 32];
+  const int f = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y_first = blockIdx.y * kFastTileH + warp * kFastRows;
+  const int nrows = min(kFastRows, H - y_first);
+  if (nrows <= 0) return;
+  PixelSink sink;
+  sink.base = frames_out + (size_t)f * H * W * 3;
+  sink.pitch = (unsigned)W * 3u; sink.ox = 0; sink.oy = 0;
+  warp_rows<false>(frames_in + (size_t)f * H * W * 3, T, f, W, H, blockIdx.x * kTileW, y_first, nrows, 0, W - 1, sink, 0u,
+                   border, scratch[warp].med, scratch[warp].ex, scratch[warp].slow, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused pass B: stabilized tile in shared memory -> cv2.resize of the crop window (mfs.py:1111-1157)
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef MF_FUSED_TILE_H
+#define MF_FUSED_TILE_H 64
+#endif
+static constexpr int kOutTileW = 120;                       // final-frame pixels per CTA: 30 groups of four
+static constexpr int kOutTileH = MF_FUSED_TILE_H;           // eight rows per warp in the resize phase
+static_assert(kOutTileH % 8 == 0 && kOutTileH >= 8 && kOutTileH <= 120, "resize phase: whole rows per warp");
+static constexpr int kStabRows = kOutTileH + 1;             // scale <= 1: at most one source row more than output rows
+static constexpr int kStabRowsPerWarp = (kStabRows + 7) / 8;
+static constexpr int kStabPitch = kTileW * 3;               // 384 B: 128 stabilized pixels per row
+static_assert(kStabRowsPerWarp <= 16 && kStabRowsPerWarp * 8 >= kStabRows, "rows of the stabilized tile split over eight warps");
+
+struct FusedShared {
+  uint8_t tile[kStabRows * kStabPitch + 32];               // + slack: a zero-weight tap may read past the last pixel
+  WarpScratch<kStabRowsPerWarp> scratch[kWarpThreads / 32];
+};
+
+// Horizontal pass of cv2.resize for the four pixels of a thread on one row of the shared-memory tile:
+// (a0 * p[c0] + a1 * p[c0 + 1]) >> 4 per channel.  boff[j] = byte offset of pixel j's left tap in the row.
+__device__ __forceinline__ void fused_hsum(unsigned row_shared, const unsigned (&woff)[kPix], const unsigned (&shift)[kPix],
+                                           const uint32_t (&wx)[kPix], RowSums& out) {
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    uint32_t t0, t1, t2;
+    const unsigned a = row_shared + woff[j];
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t0) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(t1) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(t2) : "r"(a));
+    const uint32_t u0 = __funnelshift_r(t0, t1, shift[j]), u1 = __funnelshift_r(t1, t2, shift[j]);   // B0 G0 R0 B1 | G1 R1 . .
+    const uint32_t bg = __byte_perm(u0, u1, 0x4130), rr = __byte_perm(u0, u1, 0x0052);
+    out.v[j][0] = __dp2a_lo(wx[j], bg, 0u) >> 4;
+    out.v[j][1] = __dp2a_hi(wx[j], bg, 0u) >> 4;
+    out.v[j][2] = __dp2a_lo(wx[j], rr, 0u) >> 4;
+  }
+}
+
+#ifndef MF_FUSED_MINBLOCKS
+#define MF_FUSED_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_kernel(
+    const uint8_t* __restrict__ frames_in, uint8_t* __restrict__ frames_out, const WarpTables T, int table_frame0, int W, int H,
+    uint32_t border, const int32_t* __restrict__ enc4, const int4* __restrict__ xtab, const int4* __restrict__ ytab) {
+  extern __shared__ __align__(16) unsigned char fused_raw[];
+  FusedShared& sm = *reinterpret_cast<FusedShared*>(fused_raw);
+  int left, top, right, bottom;
+  if (!decode_crop(enc4, W, H, left, top, right, bottom)) return;      // host raises once it reads the rectangle back
+  const int fl = blockIdx.z;                                 // frame within this call
+  const int f = table_frame0 + fl;                           // frame within the tables
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ox0 = blockIdx.x * kOutTileW, oy0 = blockIdx.y * kOutTileH;
+  const int ox1 = min(W, ox0 + kOutTileW) - 1, oy1 = min(H, oy0 + kOutTileH) - 1;
+  // stabilized pixels this tile's taps touch (crop-relative tap indices from the resize tables)
+  const int xa = left + __ldg(xtab + ox0).x, xb = min(right, left + __ldg(xtab + ox1).x + 1);
+  const int ya = top + __ldg(ytab + oy0).x, yb = top + __ldg(ytab + oy1).y;
+  const int X0 = xa & ~3;
+  const uint8_t* src = frames_in + (size_t)fl * H * W * 3;
+  const unsigned tile_shared = (unsigned)__cvta_generic_to_shared(sm.tile);
+  {
+    PixelSink sink;
+    sink.base = sm.tile; sink.pitch = kStabPitch; sink.ox = X0; sink.oy = ya;
+    const int y_first = ya + warp * kStabRowsPerWarp;
+    const int nrows = min(kStabRowsPerWarp, yb - y_first + 1);
+#ifdef MF_EXP_NO_WARP                  // timing experiment only: cost of the resize phase alone
+    if (false)
+#else
+    if (nrows > 0)
+#endif
+      warp_rows<true>(src, T, f, W, H, X0, y_first, nrows, xa, xb, sink, tile_shared, border, sm.scratch[warp].med,
+                      sm.scratch[warp].ex, sm.scratch[warp].slow, lane);
+  }
+  __syncthreads();
+#ifdef MF_EXP_NO_RESIZE                // timing experiment only: cost of the stabilization phase alone
+  if (sm.tile[threadIdx.x] != 7 || true) return;
+#endif
+  // ---- resize phase: warp = 8 output rows x 120 pixels, four adjacent output pixels per thread ----
+  const int px0 = ox0 + lane * kPix;
+  if (lane * kPix >= kOutTileW || px0 > ox1) return;
+  const int y_out0 = oy0 + warp * (kOutTileH / 8);
+  const int y_out1 = min(oy1, y_out0 + kOutTileH / 8 - 1);
+  if (y_out0 > y_out1) return;
+  const int npx = min(kPix, ox1 - px0 + 1);
+  const unsigned out_pitch = (unsigned)W * 3u;
+  uint8_t* drow = frames_out + ((size_t)fl * H * W + (size_t)y_out0 * W + px0) * 3;
+  uint32_t wx[kPix];
+  unsigned woff[kPix], shift[kPix];
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    const int4 xt = __ldg(xtab + min(px0 + j, W - 1));
+    // the right tap of a pixel clamped at the crop's last column carries weight 0: reading c0 + 1 is harmless
+    wx[j] = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
+    const unsigned b = (unsigned)(left + xt.x - X0) * 3u;
+    woff[j] = b & ~3u; shift[j] = (b & 3u) * 8u;
+  }
+  const bool word_store = npx == kPix && (out_pitch & 3u) == 0u && (reinterpret_cast<uintptr_t>(drow) & 3u) == 0u;
+  RowSums P, Q;
+  int rp = -1, rq = -1;
+  bool swapped = false;                                      // false: P is the top row, Q the bottom row
+  auto vertical = [&](const RowSums& Tt, const RowSums& M, const int4& yt) {
+    const uint32_t b0s = (uint32_t)yt.z << 16, b1s = (uint32_t)yt.w << 16;
+    uint32_t v[kPix][3];
+#pragma unroll
+    for (int jj = 0; jj < kPix; ++jj)
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)   // a0 + a1 <= 2049 and b0 + b1 <= 2049 bound the result by 255: no clamp needed
+        v[jj][ch] = (__umulhi(b0s, Tt.v[jj][ch]) + __umulhi(b1s, M.v[jj][ch]) + 2u) >> 2;
+    if (word_store) {
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
+      __stcs(d32 + 0, __byte_perm(__byte_perm(v[0][0], v[0][1], 0x0040), __byte_perm(v[0][2], v[1][0], 0x0040), 0x5410));
+      __stcs(d32 + 1, __byte_perm(__byte_perm(v[1][1], v[1][2], 0x0040), __byte_perm(v[2][0], v[2][1], 0x0040), 0x5410));
+      __stcs(d32 + 2, __byte_perm(__byte_perm(v[2][2], v[3][0], 0x0040), __byte_perm(v[3][1], v[3][2], 0x0040), 0x5410));
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < kPix; ++jj)
+        if (jj < npx) { drow[3 * jj] = (uint8_t)v[jj][0]; drow[3 * jj + 1] = (uint8_t)v[jj][1]; drow[3 * jj + 2] = (uint8_t)v[jj][2]; }
+    }
+  };
+  // Tt holds source row rt in the top role, M holds rm in the bottom role; returns true when the roles swapped
+  auto step = [&](RowSums& Tt, RowSums& M, int& rt, int& rm, int r0, int r1, const int4& yt) -> bool {
+    if (r0 != rt && r0 == rm && r1 != rm) {                  // the usual move: old bottom becomes top, one new row
+      fused_hsum(tile_shared + (unsigned)(r1 - ya) * kStabPitch, woff, shift, wx, Tt);
+      rt = r1;
+      vertical(M, Tt, yt);
+      return true;
+    }
+    if (r0 != rt) {
+      if (r0 == rm) Tt = M; else fused_hsum(tile_shared + (unsigned)(r0 - ya) * kStabPitch, woff, shift, wx, Tt);
+      rt = r0;
+    }
+    if (r1 != rm) {
+      if (r1 == rt) M = Tt; else fused_hsum(tile_shared + (unsigned)(r1 - ya) * kStabPitch, woff, shift, wx, M);
+      rm = r1;
+    }
+    vertical(Tt, M, yt);
+    return false;
+  };
+#ifndef MF_FUSED_NO_PROLOGUE
+  {
+    // prologue: the first output row's top source row enters in the bottom role, so that the first step is already
+    // "the usual move" (one new row) and the general form stays out of the common path
+    rq = top + __ldg(ytab + y_out0).x;
+    fused_hsum(tile_shared + (unsigned)(rq - ya) * kStabPitch, woff, shift, wx, Q);
+  }
+#endif
+  for (int py = y_out0; py <= y_out1; ++py, drow += out_pitch) {
+    const int4 yt = __ldg(ytab + py);
+    const int r0 = top + yt.x, r1 = top + yt.y;              // warp-uniform
+    const bool flip = swapped ? step(Q, P, rq, rp, r0, r1, yt) : step(P, Q, rp, rq, r0, r1, yt);
+    swapped = swapped != flip;
   }
 }
 

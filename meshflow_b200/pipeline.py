@@ -159,16 +159,42 @@ class DeviceCore:
         return (dst, crop, maps) if return_maps else (dst, crop)
 
     @_on_device
-    def warp_crop_bounds(self, u, s):
-        """Per-frame crop edges (nf,4) int32 exactly as ``warp_frames`` returns them, computed from the
-        vertex paths alone (no pixel is read): pass A of the streamed schedule."""
+    def warp_prepare(self, u, s, key="warp"):
+        """Pass A: per-frame crop edges (nf,4) int32 exactly as ``warp_frames`` returns them, computed from the
+        vertex paths alone (no pixel is read), plus the row-segment tables of these nf frames, which stay in
+        the core's workspace ``key`` for ``warp_resize_frames``.  Returns (crop, tables handle)."""
         m = self.mesh
         nf = int(u.shape[0])
         crop = torch.empty((nf, 4), dtype=torch.int32, device=self.device)
-        ws = self._workspace("warp", self.lib.mf_warp_workspace_bytes(nf, m.width, m.height, m.rows, m.cols))
-        _cabi.check(self.lib.mf_warp_crop_bounds(_ptr(u), _ptr(s), _ptr(self.vertex_xy), nf, m.width, m.height,
-                                                 m.rows, m.cols, _ptr(crop), _ptr(ws), ws.numel(), self._stream()))
-        return crop
+        ws = self._workspace(key, self.lib.mf_warp_workspace_bytes(nf, m.width, m.height, m.rows, m.cols))
+        _cabi.check(self.lib.mf_warp_prepare(_ptr(u), _ptr(s), _ptr(self.vertex_xy), nf, m.width, m.height,
+                                             m.rows, m.cols, _ptr(crop), _ptr(ws), ws.numel(), self._stream()))
+        return crop, (ws, nf)
+
+    def warp_crop_bounds(self, u, s):
+        """Round-1 name of pass A: only the per-frame crop edges."""
+        return self.warp_prepare(u, s)[0]
+
+    @_on_device
+    def warp_resize_frames(self, frames, crop_enc, tables, first_frame=0, out=None):
+        """Pass B, fused: frames ``first_frame ..`` of the video ``tables`` was prepared for -> cropped frames
+        stretched back to the frame size, one kernel, no stabilized intermediate in DRAM."""
+        m = self.mesh
+        nf = int(frames.shape[0])
+        dst = torch.empty_like(frames) if out is None else out
+        ws, table_frames = tables
+        rws = self._workspace("resize", self.lib.mf_crop_resize_workspace_bytes(m.width, m.height))
+        b, g, r = self.border_bgr
+        _cabi.check(self.lib.mf_warp_resize_frames(
+            _ptr(frames), nf, int(first_frame), int(table_frames), m.width, m.height, m.rows, m.cols, b, g, r,
+            _ptr(crop_enc), _ptr(dst), _ptr(ws), ws.numel(), _ptr(rws), rws.numel(), self._stream()))
+        return dst
+
+    @property
+    def fused_pass_available(self):
+        """The fused kernel needs the row-segment tables (frames at least 16 pixels wide)."""
+        m = self.mesh
+        return m.width >= 16 and m.height >= 2 and m.width <= 32767 and m.height <= 32767 and m.rows * m.cols < 0xfffd
 
     @_on_device
     def combine_crop(self, per_frame_crop):
@@ -208,11 +234,16 @@ class DeviceCore:
                                             _ptr(ws), ws.numel(), self._stream()))
         return dst
 
-    @_on_device
-    def warp_crop_resize(self, frames, u, s, crop_enc, out=None):
+    def warp_crop_resize(self, frames, u, s, crop_enc, out=None, tables=None, first_frame=0):
         """Pass B of the streamed schedule: frames + displacements + the (already known) crop rectangle ->
-        cropped frames stretched back to the frame size (mfs.py:909-1100 followed by 1111-1157)."""
+        cropped frames stretched back to the frame size (mfs.py:909-1100 followed by 1111-1157).  ``tables``:
+        handle of a ``warp_prepare`` call that covered these frames (they are rebuilt for the chunk otherwise)."""
         nf = int(frames.shape[0])
+        if self.fused_pass_available:
+            if tables is None:
+                _, tables = self.warp_prepare(u, s, key="warp_chunk")
+                first_frame = 0
+            return self.warp_resize_frames(frames, crop_enc, tables, first_frame, out=out)
         key = ("stab", tuple(frames.shape[1:]))
         buf = self._ws.get(key)
         if buf is None or buf.shape[0] < nf:
@@ -250,9 +281,10 @@ class StreamedCore:
 
     N_SLOTS = 3
 
-    def __init__(self, core: DeviceCore, chunk_frames=16):
+    def __init__(self, core: DeviceCore, chunk_frames=16, table_budget_bytes=4 << 30):
         self.core = core
         self.chunk = int(chunk_frames)
+        self.table_budget_bytes = int(table_budget_bytes)
         dev = core.device
         self.copy_in = torch.cuda.Stream(device=dev)
         self.copy_out = torch.cuda.Stream(device=dev)
@@ -267,19 +299,27 @@ class StreamedCore:
         return self._bufs[1], self._bufs[2]
 
     def crop_of_video(self, u, s, plan=None):
-        """Pass A: encoded crop rectangle of the whole video from the vertex paths of THIS rank's frames,
-        evaluated chunk by chunk (scratch stays O(chunk)), then one MAX all-reduce across the plan."""
+        """Pass A: encoded crop rectangle of the whole video from the vertex paths of THIS rank's frames, then
+        one MAX all-reduce across the plan.  When the row-segment tables of all frames fit ``table_budget_bytes``
+        they are built once and kept for pass B (returned handle); longer videos are evaluated chunk by
+        chunk (scratch stays O(chunk)) and pass B rebuilds the tables of each chunk."""
         from . import distributed as mfd
         core = self.core
-        enc = None
-        step = max(self.chunk, 64)
-        for f0 in range(0, int(u.shape[0]), step):
-            part = core.combine_crop(core.warp_crop_bounds(u[f0:f0 + step], s[f0:f0 + step]))
-            enc = part if enc is None else torch.maximum(enc, part)
+        m = core.mesh
+        enc, tables = None, None
+        F = int(u.shape[0])
+        if F and core.lib.mf_warp_workspace_bytes(F, m.width, m.height, m.rows, m.cols) <= self.table_budget_bytes:
+            crop, tables = core.warp_prepare(u, s)
+            enc = core.combine_crop(crop)
+        else:
+            step = max(self.chunk, 64)
+            for f0 in range(0, F, step):
+                part = core.combine_crop(core.warp_prepare(u[f0:f0 + step], s[f0:f0 + step], key="warp_chunk")[0])
+                enc = part if enc is None else torch.maximum(enc, part)
         if enc is None:       # a rank without frames contributes the identity of the max-reduction
             m = core.mesh
             enc = torch.tensor([0, 0, -(m.width - 1), -(m.height - 1)], dtype=torch.int32, device=core.device)
-        return mfd.reduce_crop(enc, plan)
+        return mfd.reduce_crop(enc, plan), tables
 
     def run(self, h_frames, tracks, h_out, definition, plan=None, d_frames=None, on_chunk_landed=None,
             return_homographies=False):
@@ -315,7 +355,7 @@ class StreamedCore:
             if int(u.shape[0]) != F or int(s.shape[0]) != F:
                 raise ValueError(f"paths cover {int(u.shape[0])} of this rank's {F} frames")
             # 2. crop rectangle of the whole video
-            enc = self.crop_of_video(u, s, plan)
+            enc, tables = self.crop_of_video(u, s, plan)
             # 3. chunked, triple-buffered pixel pass
             n_slots = self.N_SLOTS
             in_ready = [torch.cuda.Event() for _ in range(n_slots)]
@@ -338,7 +378,8 @@ class StreamedCore:
                     src = d_frames[f0:f0 + n]
                 if out_free[slot] is not None:
                     main.wait_event(out_free[slot])                 # the D2H that last read this slot is done
-                core.warp_crop_resize(src, u[f0:f0 + n], s[f0:f0 + n], enc, out=outs[slot][:n])
+                core.warp_crop_resize(src, u[f0:f0 + n], s[f0:f0 + n], enc, out=outs[slot][:n], tables=tables,
+                                      first_frame=f0)
                 if d_frames is None:
                     e = torch.cuda.Event(); e.record(main); in_free[slot] = e
                 out_ready[slot].record(main)

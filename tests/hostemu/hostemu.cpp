@@ -157,6 +157,7 @@ static void emu_cells_all(const float* vertex_xy, const double* u, const double*
       mf::cell_setup(rest, stab, W, H, cells[id]);
       mf::cell_fast_setup(cells[id], (int)floor(fmin(rest[0], rest[4])), (int)ceil(fmax(rest[2], rest[6])),
                           (int)floor(fmin(rest[1], rest[3])), (int)ceil(fmax(rest[5], rest[7])), W, H, fast[id], spans[id]);
+      if (fast[id].thr_u >= 0.0f) cells[id].edge_flags |= mf::kMapMonotone;      // as cell_setup_kernel does
     }
 }
 
@@ -226,20 +227,49 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
       if (ns < 0) { out[0] = ((unsigned)x0 << 16) | mf::kSegIrregular; for (int i = 1; i < segcap; ++i) out[i] = mf::kSegSentinel; stats[3]++; }
       else for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : mf::kSegSentinel;
     }
+  // crop edges from the row segments of tiles that hold a border cell (crop_edges_kernel)
   int crop[4] = {0, 0, W - 1, H - 1};
-  std::vector<std::pair<int, int>> queue, medium;           // float64 path / per-pixel tap fetch (kernel: medmask)
+  for (int y = 0; y < H; ++y)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      const std::vector<int>& l = lists[(y / kTileH) * tiles_x + tx];
+      bool edge_tile = false;
+      for (int id : l) edge_tile = edge_tile || (cells[id].edge_flags & mf::kEdgeAny) != 0u;
+      if (!edge_tile) continue;
+      const int x0 = tx * kTileW, x1 = std::min(W - 1, x0 + kTileW - 1);
+      const unsigned* rs = &rowseg[((size_t)y * tiles_x + tx) * segcap];
+      if ((rs[0] & 0xffffu) == mf::kSegIrregular) {
+        const bool overflow = (int)l.size() > kTileCap;
+        const int n = overflow ? ncell : (int)l.size();
+        for (int px = x0; px <= x1; ++px) {
+          float mx = (float)(W + 1), my = (float)(H + 1);
+          for (int k = 0; k < n; ++k) {
+            const mf::Cell& c = cells[overflow ? ncell - 1 - k : l[k]];
+            if (px < c.bx0 || px > c.bx1 || y < c.by0 || y > c.by1) continue;
+            if (mf::cell_inside(c, (double)px, (double)y)) { mf::cell_map(c, (double)px, (double)y, mx, my); break; }
+          }
+          if (mx > -1.0f && mx < 1.0f && px > crop[0]) crop[0] = px;
+          if (my > -1.0f && my < 1.0f && y > crop[1]) crop[1] = y;
+          if (mx > (float)(W - 2) && mx < (float)W && px < crop[2]) crop[2] = px;
+          if (my > (float)(H - 2) && my < (float)H && y < crop[3]) crop[3] = y;
+        }
+        continue;
+      }
+      int ns = 0;
+      while (ns < segcap && rs[ns] != mf::kSegSentinel) ++ns;
+      for (int i = 0; i < ns; ++i) {
+        const unsigned id = rs[i] & 0xffffu;
+        if (id == mf::kSegNone) continue;
+        const int xa = (int)(rs[i] >> 16), xb = i + 1 < ns ? (int)(rs[i + 1] >> 16) - 1 : x1;
+        mf::segment_crop_edges(cells[id], xa, xb, y, W, H, crop);
+      }
+    }
+  for (int i = 0; i < 4; ++i) crop4[i] = crop[i];
+  if (bounds_only) return;
+  std::vector<std::pair<int, int>> queue, medium;           // float64 path / per-pixel tap fetch
   const int bord[3] = {bb, bg, br};
   for (int py = 0; py < H; ++py)
     for (int px0 = 0; px0 < W; px0 += 4) {
       const int npx = std::min(4, W - px0), tx = px0 / kTileW;
-      if (bounds_only) {
-        bool edge_tile = false;
-        for (int id : lists[(py / kTileH) * tiles_x + tx]) {
-          const mf::CellFast& cf = fast[id];
-          edge_tile = edge_tile || cf.flags != 0u;          // superset of the kernel's tile flag
-        }
-        if (!edge_tile) continue;
-      }
       const unsigned* rs = &rowseg[((size_t)py * tiles_x + tx) * segcap];
       bool strad;
       const unsigned id = mf::seg_group_owner(rs, segcap, px0, strad);
@@ -255,8 +285,8 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
           const unsigned bad = mf::fast_group_coords(cf.a[0], cf.a[1], cf.a[2], cf.a[3], cf.a[4], cf.a[5], cf.a[6], cf.a[7],
                                                      cf.a[8], cf.thr_u, cf.thr_v, cf.bx0, cf.by0, px0, py, nu, nv);
           stats[2] += __builtin_popcount(bad);
-          bool edge; push = mf::fast_group_plan(nu, nv, bad, cf.base_x, cf.base_y, cf.flags, W, H, bounds_only != 0, ix0, iy0, fg, edge);
-          if (push == 15u && !edge) { push = bad; med = 15u & ~bad; }
+          bool edge; push = mf::fast_group_plan(nu, nv, bad, cf.base_x, cf.base_y, 0u, W, H, false, ix0, iy0, fg, edge);
+          if (push == 15u) { push = bad; med = 15u & ~bad; }
         }
       }
       if (push == 15u || (npx < 4 && push)) stats[5]++;
@@ -285,7 +315,7 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
     const mf::CellFast& cf = fast[id];
     int sx, sy;
     if (!mf::medium_coords(cf.a[0], cf.a[1], cf.a[2], cf.a[3], cf.a[4], cf.a[5], cf.a[6], cf.a[7], cf.a[8], cf.thr_u, cf.thr_v,
-                           cf.bx0, cf.by0, cf.base_x, cf.base_y, cf.flags, px, py, W, H, sx, sy)) { queue.push_back(q); continue; }
+                           cf.bx0, cf.by0, cf.base_x, cf.base_y, 0u, px, py, W, H, sx, sy)) { queue.push_back(q); continue; }
     if (!bounds_only) mf::remap_pixel(src, W, H, sx >> 5, sy >> 5, sx & 31, sy & 31, bb, bg, br, dst + ((size_t)py * W + px) * 3);
   }
   stats[1] = (long long)queue.size();
@@ -305,16 +335,10 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
     } else if (id != mf::kSegNone) {
       mf::cell_map(cells[id], (double)px, (double)py, mx, my);
     }
-    if (mx > -1.0f && mx < 1.0f && px > crop[0]) crop[0] = px;
-    if (my > -1.0f && my < 1.0f && py > crop[1]) crop[1] = py;
-    if (mx > (float)(W - 2) && mx < (float)W && px < crop[2]) crop[2] = px;
-    if (my > (float)(H - 2) && my < (float)H && py < crop[3]) crop[3] = py;
-    if (bounds_only) continue;
     int ix, iy, ax, ay;
     mf::remap_coords(mx, my, ix, iy, ax, ay);
     mf::remap_pixel(src, W, H, ix, iy, ax, ay, bb, bg, br, dst + ((size_t)py * W + px) * 3);
   }
-  for (int i = 0; i < 4; ++i) crop4[i] = crop[i];
 }
 
 

@@ -203,6 +203,53 @@ def test_warp_fast_path_equals_generic_kernel_on_camera_like_warps(W, H, R, C):
     assert torch.equal(core.warp_crop_bounds(_dev(u, core), _dev(s, core)), crop_gen)
 
 
+def _camera_like(rng, W, H, R, C, F, rough=0.1):
+    rest = spec.vertex_xy(W, H, R, C).astype(np.float64)
+    d = np.zeros((F, (R + 1) * (C + 1), 2))
+    for f in range(F):
+        Hm = synth.random_homography(rng, W, H, rot=0.004 * (1 + 3 * f), scale=0.003 * (1 + 3 * f), trans=4.0 * (1 + f))
+        w = rest[:, 0] * Hm[2, 0] + rest[:, 1] * Hm[2, 1] + 1.0
+        d[f, :, 0] = (rest[:, 0] * Hm[0, 0] + rest[:, 1] * Hm[0, 1] + Hm[0, 2]) / w - rest[:, 0]
+        d[f, :, 1] = (rest[:, 0] * Hm[1, 0] + rest[:, 1] * Hm[1, 1] + Hm[1, 2]) / w - rest[:, 1]
+    d += rng.normal(0, rough, d.shape)
+    return np.zeros((F, R + 1, C + 1, 2)), d.reshape(F, R + 1, C + 1, 2)
+
+
+@pytest.mark.parametrize("W,H,R,C,rough", [(1920, 1080, 16, 16, 0.1), (1280, 720, 64, 64, 0.05), (333, 217, 6, 9, 1.5),
+                                           (3840, 2160, 32, 32, 0.1), (640, 360, 16, 16, 4.0), (200, 120, 4, 6, 8.0),
+                                           (130, 70, 4, 4, 0.3)])
+def test_fused_pass_equals_warp_then_resize(W, H, R, C, rough):
+    """Pass B in one kernel (stabilized tile in shared memory, resized from there) against the two-kernel
+    sequence warp_frames -> crop_resize, bit for bit, for the video's own crop rectangle and for hand-picked
+    ones: the whole frame (scale 1: every tile needs its one extra row and column), a tight crop, and crops
+    that put tile borders at odd phases."""
+    rng = np.random.default_rng(W + 7 * C)
+    F = 3
+    frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+    u, s = _camera_like(rng, W, H, R, C, F, rough)
+    core = _core(W, H, R, C, border_bgr=(5, 120, 250))
+    fd, ud, sd = _dev(frames, core), _dev(u, core), _dev(s, core)
+    stab, crop_pf = core.warp_frames(fd, ud, sd)
+    crop_a, tables = core.warp_prepare(ud, sd)
+    assert torch.equal(crop_a, crop_pf)
+    own = core.decode_crop(core.combine_crop(crop_pf))
+    crops = [(0, 0, W - 1, H - 1), (W // 5, H // 7, W - 1 - W // 6, H - 1 - H // 5), (1, 2, W - 4, H - 3),
+             (W // 3, H // 3, W // 3 + max(8, W // 4), H // 3 + max(8, H // 4))]
+    if own[0] <= own[2] and own[1] <= own[3]:
+        crops.append(own)
+    for (l, t, r, b) in crops:
+        enc = torch.tensor([l, t, -r, -b], dtype=torch.int32, device=core.device)
+        ref = core.crop_resize_device(stab, enc)
+        got = core.warp_resize_frames(fd, enc, tables)
+        assert torch.equal(got, ref), f"crop {(l, t, r, b)}: {(got != ref).any(dim=3).sum().item()} px differ"
+        # a chunk in the middle of the prepared video
+        part = core.warp_resize_frames(fd[1:3], enc, tables, first_frame=1)
+        assert torch.equal(part, ref[1:3])
+    # tables rebuilt per chunk (what long videos do) give the same frames
+    enc = torch.tensor([crops[1][0], crops[1][1], -crops[1][2], -crops[1][3]], dtype=torch.int32, device=core.device)
+    assert torch.equal(core.warp_crop_resize(fd[2:3], ud[2:3], sd[2:3], enc), core.crop_resize_device(stab, enc)[2:3])
+
+
 def test_warp_many_frames_back_to_back_on_one_workspace():
     """70 frames per call, three calls in a row on the same workspace (different displacements in between): same
     frames and crop edges as the generic kernel every time."""

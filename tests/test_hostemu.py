@@ -191,6 +191,46 @@ def test_fast_warp_path_identity_and_folded_mesh(emu):
     assert tuple(crop.tolist()) == spec.crop_edges(mx, my)
 
 
+def _crop_by_segments(emu, W, H, R, C, d):
+    rest = spec.vertex_xy(W, H, R, C)
+    zero = np.zeros_like(d)
+    crop = np.zeros(4, np.int32); stats = np.zeros(6, np.int64)
+    emu.emu_warp_frame_fast(None, P(rest), P(zero), P(np.ascontiguousarray(d)), W, H, R, C, 0, 0, 255, None, P(crop), 1, P(stats))
+    return crop.tolist()
+
+
+def _crop_by_scan(W, H, R, C, d):
+    sc = spec.cell_setup(spec.vertex_xy(W, H, R, C), d, R, C)
+    mx, my, _ = spec.warp_maps(W, H, sc, prune=False)
+    return list(spec.crop_edges(mx, my))
+
+
+@pytest.mark.parametrize("W,H,R,C", [(320, 180, 8, 8), (640, 360, 16, 16), (333, 217, 6, 9)])
+def test_crop_edges_from_row_segments_equal_the_pixel_scan(emu, W, H, R, C):
+    """The closed-form band search on row segments (crop_edges_kernel) against the reference's scan of the
+    float32 maps (mfs.py:1075-1098): pure translations (the map is constant along a row: zero slope), integer
+    and half-pixel shifts that put map values exactly ON a band limit, large shifts in all four directions,
+    rotation / scale / perspective, rough per-vertex noise."""
+    rng = np.random.default_rng(W + R)
+    V = (R + 1) * (C + 1)
+    rest = spec.vertex_xy(W, H, R, C).astype(np.float64)
+    cases = []
+    for shift in [(0.0, 0.0), (7.0, -5.0), (-3.0, 4.0), (0.5, 0.5), (-0.5, 1.0), (1.0, -1.0), (12.25, 9.75), (-17.5, -6.125),
+                  (0.96875, -0.96875), (1.03125, 0.984375)]:
+        cases.append(np.tile(np.array(shift), (V, 1)))
+    for k in range(6):
+        Hm = synth.random_homography(rng, W, H, rot=0.01 * (k + 1), scale=0.01 * (k + 1), trans=3.0 * (k + 1), persp=3e-6 * k)
+        w = rest[:, 0] * Hm[2, 0] + rest[:, 1] * Hm[2, 1] + 1.0
+        moved = np.stack([(rest[:, 0] * Hm[0, 0] + rest[:, 1] * Hm[0, 1] + Hm[0, 2]) / w,
+                          (rest[:, 0] * Hm[1, 0] + rest[:, 1] * Hm[1, 1] + Hm[1, 2]) / w], axis=1)
+        cases.append(moved - rest + rng.normal(0, 0.05 * k, rest.shape))
+    for amp in (1.0, 4.0, 12.0):
+        cases.append(rng.normal(0, amp, (V, 2)) + rng.normal(0, 2 * amp, (1, 2)))
+    for d in cases:
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        assert _crop_by_segments(emu, W, H, R, C, d) == _crop_by_scan(W, H, R, C, d)
+
+
 def test_segment_resolution_matches_brute_force(emu):
     """'The last cell written wins': random overlapping intervals in priority order against a per-pixel loop."""
     rng = np.random.default_rng(5)
