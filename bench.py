@@ -1,24 +1,40 @@
 #!/usr/bin/env python
 """Benchmark of the MeshFlow stabilization hot path on B200 (and the CPU reference arm).
 
-A *step* is one pass of the hot path (vertex-motion estimation -> float64 prefix sum -> Jacobi path
-optimisation -> per-cell homography warp -> crop combine -> crop/resize -> stability score) over one
-batch: BASELINE.json configs[1], a synthetic 1080p 300-frame jittered video, 16x16 mesh, radius 10,
-100 Jacobi iterations.  The OpenCV front end (FAST / LK / RANSAC / global homography) is the
-reference's own host code on both arms and runs once, outside the timed region, to produce the tracks.
+Default (``--config c2`` = BASELINE.json configs[1]): a *step* is one pass of the hot path over one synthetic
+1080p 300-frame jittered video, 16x16 mesh, radius 10, 100 Jacobi iterations:
 
-  value : whole-job frames/s with frames + tracks already resident in HBM (CUDA events, max over ranks)
-  e2e   : frames/s through the host-facing call: pinned HOST frames + tracks -> H2D -> hot path ->
-          D2H of the cropped frames, all inside the timed region
-  roofline : the warp kernel (dominant), algorithmic bytes 6*H*W per frame over its CUDA-event time,
-          against MEASURED_PEAKS.json's HBM copy bandwidth
-  cpu_baseline : the oracle port (oracle/reference_port.py: same OpenCV/NumPy calls as the reference)
-          timed on this box's host cores on a bounded sample (rank 0, N=1 only)
+    vertex-motion estimation -> float64 prefix sum -> Jacobi path optimisation          ("paths")
+    -> cell homographies, row segments, analytic crop edges (no pixel read)              ("prepare")
+    -> crop combine -> fused mesh warp + crop + resize                                   ("pixel pass")
+    -> stability score
 
-`--impl reference` times only that CPU port (the reference arm).  Under torchrun (N>1) every rank owns
-`--frames` frames of an N*frames-frame video (weak scaling): velocities are all-gathered, the Jacobi
-solve is vertex-sharded, the solved paths all-gathered, frames warped locally and the crop rectangle
-combined with one ncclMax all-reduce.
+The OpenCV front end (FAST / LK / RANSAC / global homography) is the reference's own host code on both arms and
+runs once, outside the timed region, to produce the tracks.
+
+  value    : whole-job frames/s with frames + tracks already resident in HBM (CUDA events, max over ranks)
+  e2e      : frames/s through the host-facing core call: pinned HOST frames + tracks -> H2D -> hot path -> D2H of
+             the cropped frames, all inside the timed region (StreamedCore.run)
+  e2e_api  : frames/s of the drop-in API itself, MeshFlowStabilizer.stabilize_frames(): host tracking, staging,
+             GPU passes and metric tracking included (wall clock; rank 0, N=1 only)
+  roofline : the fused pixel kernel (dominant): algorithmic bytes 6*H*W per frame over its own CUDA-event time,
+             against MEASURED_PEAKS.json's HBM copy bandwidth; traffic = ncu dram bytes (profiles/)
+  jacobi   : the Jacobi solve alone: HBM GB/s (32*V*F bytes) and float64 TFLOP/s
+  cpu_baseline : the reference's algorithm timed on this box's host cores on a bounded sample (rank 0, N=1):
+             the UNMODIFIED reference (baseline/_ref, kind "reference") when staged, else the oracle port
+  parity_checked : outside the timed region -- fused == two-kernel on every frame, production == generic pixel
+             kernel on every frame, and the CPU leg fed with the GPU's own paths reproduces the GPU's frames
+
+``--impl reference`` times only the CPU arm.  Under torchrun (N>1) every rank owns ``--frames`` frames of an
+N*frames-frame video (weak scaling): velocities + homographies are all-gathered in one exchange, the Jacobi solve
+is vertex-sharded, the solved paths all-gathered, frames warped locally and the crop rectangle combined with one
+ncclMax all-reduce.
+
+Other BASELINE.json configurations (one JSON line each, kept under profiles/):
+  --config c3 : 4K x 1000 frames, 32x32 mesh, CONSTANT_HIGH, frame-sharded over the ranks (strong scaling), host
+                frames in / out through the streamed schedule
+  --config c4 : Jacobi only, 64x64 mesh x 10 000 frames, radius 30, 500 iterations, vertex-sharded (strong scaling)
+  --config c5 : warp-only sweep 720p -> 8K with 16x16 and 64x64 meshes, every rank its own frames (weak scaling)
 """
 from __future__ import annotations
 
@@ -42,21 +58,35 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=300)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--mesh", type=int, default=16)
-    ap.add_argument("--radius", type=int, default=10)
-    ap.add_argument("--iters", type=int, default=100)
-    ap.add_argument("--definition", type=int, default=0)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU (c2: 300) / total frames (c3: 1000, c4: 10000)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--mesh", type=int, default=None)
+    ap.add_argument("--radius", type=int, default=None)
+    ap.add_argument("--iters", type=int, default=None)
+    ap.add_argument("--definition", type=int, default=None)
     ap.add_argument("--tracks", default="real", choices=["real", "synthetic"],
                     help="real = run the host OpenCV front end on the synthetic video (outside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the e2e_api measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity self-checks")
+    ap.add_argument("--quick", action="store_true", help="kernel tuning: --no-cpu-baseline --no-api --no-parity")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the streamed (e2e) schedule")
     ap.add_argument("--pixel-path", default="fused", choices=["fused", "two-kernel"],
                     help="fused = prepare (tables + crop) -> one warp+crop+resize kernel; two-kernel = round-1 sequence")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_api = args.no_parity = True
+    defaults = {"c2": dict(frames=300, width=1920, height=1080, mesh=16, radius=10, iters=100, definition=0),
+                "c3": dict(frames=1000, width=3840, height=2160, mesh=32, radius=10, iters=100, definition=2),
+                "c4": dict(frames=10000, width=1920, height=1080, mesh=64, radius=30, iters=500, definition=0),
+                "c5": dict(frames=64, width=1920, height=1080, mesh=16, radius=10, iters=100, definition=0)}[args.config]
+    for k, v in defaults.items():
+        if getattr(args, k) is None:
+            setattr(args, k, v)
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
@@ -64,17 +94,16 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 def make_workload(args, rank):
     """Frames of this rank's segment (+1 look-ahead frame for its last pair) and their tracks."""
-    from tests import synth
-    from meshflow_b200 import host_features
+    from meshflow_b200 import host_features, workloads
     from meshflow_b200.stabilizer import MeshFlowStabilizer
     rng = np.random.default_rng(args.seed + 7919 * rank)
     n = args.frames
-    frames = synth.textured_video(rng, n + 1, args.width, args.height)
+    frames = workloads.textured_video(rng, n + 1, args.width, args.height)
     if args.tracks == "real":
         tracks = host_features.track_all_pairs(frames[:-1], frames[1:])
         packed = MeshFlowStabilizer.pack_tracks(tracks)
     else:
-        packed = synth.synthetic_tracks(rng, n, 3000, args.width, args.height)
+        packed = workloads.synthetic_tracks(rng, n, 3000, args.width, args.height)
     return frames[:n], packed
 
 
@@ -121,85 +150,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU arm (oracle port = the reference's algorithm and library calls)
-# ------------------------------------------------------------------------------------------------
-def cpu_hot_path_fps(args, frames, packed, warp_frames=2, vm_pairs=16):
-    """Times the port on a bounded sample of the same workload and extrapolates per-frame costs
-    (every stage's cost per frame / per pair is constant; Jacobi is timed in full)."""
-    import cv2
-    from oracle import reference_port as port
-    p = port.Params(mesh_row_count=args.mesh, mesh_col_count=args.mesh,
-                    temporal_smoothing_radius=args.radius, optimization_num_iterations=args.iters)
-    W, H, F = args.width, args.height, len(frames)
-    starts = packed["pair_start"]
-    t0 = time.perf_counter()
-    vels = []
-    npairs = min(vm_pairs, len(starts) - 1)
-    for i in range(npairs):
-        a, b = starts[i], starts[i + 1]
-        k = packed["keep"][a:b].astype(bool)
-        off = packed["offset"][a:b][k].astype(np.float64)
-        e = (packed["early"][a:b][k].astype(np.float64) + off)[:, None, :]
-        l = (packed["late"][a:b][k].astype(np.float64) + off)[:, None, :]
-        vels.append(port.vertex_velocities_from_matches(p, W, H, e, l, packed["homographies"][i]))
-    t_vm = (time.perf_counter() - t0) / max(npairs, 1)
-    rng = np.random.default_rng(5)
-    u = np.cumsum(rng.normal(0, 1.0, (F, args.mesh + 1, args.mesh + 1, 2)), axis=0)
-    homs = np.concatenate([packed["homographies"][:F - 1], np.eye(3)[None]])
-    t0 = time.perf_counter()
-    s = port.stabilized_displacements(p, W, H, args.definition, u, homs)
-    t_jac = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    stab, crop = port.warp_frames_and_crop(p, frames[:warp_frames], u[:warp_frames], s[:warp_frames])
-    t_warp = (time.perf_counter() - t0) / warp_frames
-    t0 = time.perf_counter()
-    port.crop_frames(stab, (8, 8, W - 9, H - 9))
-    t_crop = (time.perf_counter() - t0) / warp_frames
-    per_frame = t_vm + t_jac / F + t_warp + t_crop
-    return 1.0 / per_frame, {
-        "vertex_motion_s_per_pair": t_vm, "jacobi_s_total": t_jac, "warp_s_per_frame": t_warp,
-        "crop_s_per_frame": t_crop, "cores": os.cpu_count(), "cv2_threads": cv2.getNumThreads(),
-        "sample": f"vertex motion on {npairs} pairs, Jacobi in full ({F} frames), warp+crop on "
-                  f"{warp_frames} frames of {W}x{H}; per-frame costs summed and inverted"}
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def workload_name(args):
-    return (f"synthetic {args.height}p {args.frames}-frame jittered video, {args.mesh}x{args.mesh} mesh, "
-            f"radius {args.radius}, {args.iters} Jacobi iterations (BASELINE.json configs[1])")
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    frames, packed = make_workload(args, 0)
-    values = []
-    detail = None
-    for i in range(args.warmup + args.steps):
-        fps, detail = cpu_hot_path_fps(args, frames, packed, warp_frames=1, vm_pairs=4 if i < args.warmup else 16)
-        if i >= args.warmup:
-            values.append(fps)
-    v = float(np.mean(values))
-    print(json.dumps({
-        "impl": "reference", "metric": "stabilized frames/sec", "value": v, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.frames / v,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/u8", "data": "synthetic",
-        "config": {"workload": workload_name(args)},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": detail["cores"], "kind": "port",
-                         "sample": detail["sample"]},
-        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "detail": detail}))
-
-
-# ------------------------------------------------------------------------------------------------
-# GPU arm
-# ------------------------------------------------------------------------------------------------
-def run_b200(args):
+def dist_setup():
     import torch
     import torch.distributed as dist
-    from meshflow_b200 import DeviceCore, MeshSpec
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,6 +174,157 @@ def run_b200(args):
         pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(values, world, dev):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (unmodified reference when staged, else the oracle port)
+# ------------------------------------------------------------------------------------------------
+class CpuArm:
+    """Times the reference's stage methods on a bounded sample of the c2 workload and extrapolates per-frame costs
+    (every stage's cost per frame / per pair is constant; Jacobi is timed in full).  The OpenCV front end is
+    excluded on this arm too: the stages are fed the same matched features the GPU arm consumes."""
+
+    def __init__(self, args):
+        import cv2
+        from oracle import make_ref
+        self.args = args
+        self.cv2_threads = cv2.getNumThreads()
+        self.ref = make_ref.reference_module()
+        self.kind = "reference" if self.ref is not None else "port"
+        if self.ref is not None:
+            self.R = self.ref.MeshFlowStabilizer(mesh_row_count=args.mesh, mesh_col_count=args.mesh,
+                                                 temporal_smoothing_radius=args.radius,
+                                                 optimization_num_iterations=args.iters)
+        else:
+            from oracle import reference_port as port
+            self.port = port
+            self.P = port.Params(mesh_row_count=args.mesh, mesh_col_count=args.mesh,
+                                 temporal_smoothing_radius=args.radius, optimization_num_iterations=args.iters)
+
+    @staticmethod
+    def matches_of_pair(packed, i):
+        a, b = packed["pair_start"][i], packed["pair_start"][i + 1]
+        k = packed["keep"][a:b].astype(bool)
+        off = packed["offset"][a:b][k].astype(np.float64)
+        e = (packed["early"][a:b][k].astype(np.float64) + off)[:, None, :]
+        l = (packed["late"][a:b][k].astype(np.float64) + off)[:, None, :]
+        return e, l, packed["homographies"][i]
+
+    def vertex_velocities(self, frames, packed, i):
+        e, l, hom = self.matches_of_pair(packed, i)
+        if self.kind == "reference":
+            # the reference's own method with its OpenCV matching step answered from the shared tracks
+            self.R._get_matched_features_and_homography = lambda a, b: (e, l, hom)
+            return self.R._get_unstabilized_vertex_velocities(frames[i], frames[min(i + 1, len(frames) - 1)])[0]
+        return self.port.vertex_velocities_from_matches(self.P, self.args.width, self.args.height, e, l, hom)
+
+    def jacobi(self, frames, u, homs):
+        a = self.args
+        if self.kind == "reference":
+            return self.R._get_stabilized_vertex_displacements(len(u), frames, a.definition, u, homs)
+        return self.port.stabilized_displacements(self.P, a.width, a.height, a.definition, u, homs)
+
+    def warp(self, frames, u, s):
+        if self.kind == "reference":
+            return self.R._get_stabilized_frames_and_crop_boundaries(len(frames), frames, u, s)
+        return self.port.warp_frames_and_crop(self.P, frames, u, s)
+
+    def crop(self, stab, crop):
+        if self.kind == "reference":
+            return self.R._crop_frames(stab, crop)
+        return self.port.crop_frames(stab, crop)
+
+    def sample(self, frames, packed, warp_frames=1, vm_pairs=8):
+        """One bounded sample.  Returns (frames/s extrapolated, wall seconds of the sample, detail)."""
+        a = self.args
+        W, H, F = a.width, a.height, len(frames)
+        t_all = time.perf_counter()
+        npairs = min(vm_pairs, len(packed["pair_start"]) - 1)
+        t0 = time.perf_counter()
+        for i in range(npairs):
+            self.vertex_velocities(frames, packed, i)
+        t_vm = (time.perf_counter() - t0) / max(npairs, 1)
+        rng = np.random.default_rng(5)
+        u = np.cumsum(rng.normal(0, 1.0, (F, a.mesh + 1, a.mesh + 1, 2)), axis=0)
+        homs = np.concatenate([packed["homographies"][:F - 1], np.eye(3)[None]])
+        t0 = time.perf_counter()
+        s = self.jacobi(frames, u, homs)
+        t_jac = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        stab, _ = self.warp(list(frames[:warp_frames]), u[:warp_frames], s[:warp_frames])
+        t_warp = (time.perf_counter() - t0) / warp_frames
+        t0 = time.perf_counter()
+        self.crop(stab, (8, 8, W - 9, H - 9))
+        t_crop = (time.perf_counter() - t0) / warp_frames
+        wall = time.perf_counter() - t_all
+        per_frame = t_vm + t_jac / F + t_warp + t_crop
+        detail = {"vertex_motion_s_per_pair": t_vm, "jacobi_s_total": t_jac, "warp_s_per_frame": t_warp,
+                  "crop_s_per_frame": t_crop, "cores": os.cpu_count(), "cv2_threads": self.cv2_threads,
+                  "kind": self.kind,
+                  "sample": f"{'unmodified reference (baseline/_ref)' if self.kind == 'reference' else 'oracle port'}: vertex "
+                            f"motion on {npairs} pairs, Jacobi in full ({F} frames), warp+crop on {warp_frames} frame(s) of "
+                            f"{W}x{H}; per-frame costs summed and inverted"}
+        return 1.0 / per_frame, wall, detail
+
+
+def workload_name(args):
+    return (f"synthetic {args.height}p {args.frames}-frame jittered video, {args.mesh}x{args.mesh} mesh, "
+            f"radius {args.radius}, {args.iters} Jacobi iterations (BASELINE.json configs[1])")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames, packed = make_workload(args, 0)
+    arm = CpuArm(args)
+    values, walls, detail = [], [], None
+    for i in range(args.warmup + args.steps):
+        fps, wall, detail = arm.sample(frames, packed, warp_frames=1, vm_pairs=2 if i < args.warmup else 8)
+        if i >= args.warmup:
+            values.append(fps)
+            walls.append(wall)
+    v = float(np.mean(values))
+    print(json.dumps({
+        "impl": "reference", "metric": "stabilized frames/sec", "value": v, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        # wall time of one SAMPLED step (what this run really took); the extrapolated full 300-frame step is below
+        "ms_per_step": 1e3 * float(np.mean(walls)), "ms_per_full_step_extrapolated": 1e3 * args.frames / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/u8", "data": "synthetic",
+        "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": detail["cores"], "kind": detail["kind"],
+                         "sample": detail["sample"]},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "detail": detail}))
+
+
+# ------------------------------------------------------------------------------------------------
+# c2: the whole hot path
+# ------------------------------------------------------------------------------------------------
+def run_c2(args):
+    import torch
+    import torch.distributed as dist
+    from meshflow_b200 import DeviceCore, MeshSpec, StreamedCore, distributed as mfd
+
+    world, rank, local = dist_setup()
     dev = torch.device("cuda", local)
     W, H, F = args.width, args.height, args.frames
     mesh = MeshSpec(W, H, args.mesh, args.mesh)
@@ -227,74 +338,66 @@ def run_b200(args):
         h_frames[i] = torch.from_numpy(f)
     h_out = torch.empty((F, H, W, 3), dtype=torch.uint8, pin_memory=True)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    homs_pairs = packed["homographies"].reshape(-1, 9)
     h_tracks = {k: pin(packed[k]) for k in ("early", "late", "offset", "keep", "pair_start")}
-    h_tracks["homographies"] = pin(homs_pairs)
-    P = len(packed["pair_start"]) - 1          # = F pairs per rank (the look-ahead frame closes the last one)
-    last_rank = rank == world - 1
+    h_tracks["homographies"] = pin(packed["homographies"].reshape(-1, 9))
     F_total = F * world
+    plan = mfd.ShardPlan(rank, world, [F] * world) if world > 1 else None
+    host_pair_start = packed["pair_start"]
 
     d_frames = h_frames.to(dev)
     d_tracks = {k: v.to(dev) for k, v in h_tracks.items()}
     d_out = torch.empty_like(d_frames)
-    d_stab = torch.empty_like(d_frames)
-    ident = torch.eye(3, dtype=torch.float64, device=dev).reshape(1, 9)
+    fused = args.pixel_path == "fused" and core.fused_pass_available
+    d_stab = None if fused else torch.empty_like(d_frames)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    fused = args.pixel_path == "fused"
     stage_names = (["paths (vertex motion + prefix + Jacobi + exchanges)", "prepare (cells, spans, segments, crop edges)",
-                    "warp", "stability"] if fused else
-                   ["paths (vertex motion + prefix + Jacobi + exchanges)", "warp", "crop_resize", "stability"])
+                    "pixel pass (crop combine + fused warp/crop/resize)", "stability"] if fused else
+                   ["paths (vertex motion + prefix + Jacobi + exchanges)", "warp (prepare + pixel kernel)",
+                    "crop combine + resize", "stability"])
+    lo = rank * F
 
-    from meshflow_b200 import StreamedCore, distributed as mfd
-    host_pair_start = packed["pair_start"]
-    plan = mfd.ShardPlan(rank, world, [F] * world) if world > 1 else None
-
-    def hot_path(tr, frames_d, out_d, marks=None):
+    def hot_path(tr, frames_d, out_d, marks=None, keep=None):
         def mark():
             if marks is not None:
                 e = ev(); e.record(); marks.append(e)
         mark()
-        u, s, _ = mfd.sharded_paths(core, tr, F, args.definition, pair_start_host=host_pair_start, plan=plan)
+        u, s, homs = mfd.sharded_paths(core, tr, F, args.definition, pair_start_host=host_pair_start, plan=plan)
         mark()
-        lo = rank * F
         if fused:
             crop_pf, tables = core.warp_prepare(u[lo:lo + F], s[lo:lo + F])
             mark()
             enc = mfd.reduce_crop(core.combine_crop(crop_pf), plan)
             core.warp_resize_frames(frames_d, enc, tables, 0, out=out_d)
-            mark()
         else:
             _, crop_pf = core.warp_frames(frames_d, u[lo:lo + F], s[lo:lo + F], out=d_stab)
             mark()
             enc = mfd.reduce_crop(core.combine_crop(crop_pf), plan)
             core.crop_resize_device(d_stab, enc, out=out_d)
-            mark()
+        mark()
         score = core.stability_score(s)
         mark()
+        if keep is not None:
+            keep.update(u=u, s=s, homs=homs, enc=enc, crop_pf=crop_pf)
         return enc, score
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- resident-input timing --------------------------------------------------------------------
     for _ in range(args.warmup):
         hot_path(d_tracks, d_frames, d_out)
-    barrier()
+    barrier(world)
     sampler = ClockSampler(local)
     sampler.start()
     t_begin, t_end = ev(), ev()
     marks_all = []
-    barrier()
+    barrier(world)
     t_begin.record()
+    kept = {}
     for _ in range(args.steps):
         marks = []
-        enc, score = hot_path(d_tracks, d_frames, d_out, marks)
+        enc, score = hot_path(d_tracks, d_frames, d_out, marks, kept)
         marks_all.append(marks)
     t_end.record()
-    barrier()
+    barrier(world)
     clocks = sampler.stop()
     ms_total = t_begin.elapsed_time(t_end)
     stage_ms = {n: 0.0 for n in stage_names}
@@ -302,6 +405,34 @@ def run_b200(args):
         for i, n in enumerate(stage_names):
             stage_ms[n] += marks[i].elapsed_time(marks[i + 1]) / args.steps
     crop = core.decode_crop(enc)
+    u_d, s_d, homs_d = kept["u"], kept["s"], kept["homs"]
+
+    # ---- the dominant kernel and the Jacobi solve on their own (CUDA events on the launching stream) ----
+    reps = max(3, min(args.steps, 10))
+    if fused:
+        crop_pf, tables = core.warp_prepare(u_d[lo:lo + F], s_d[lo:lo + F])
+        e0, e1 = ev(), ev()
+        core.warp_resize_frames(d_frames, enc, tables, 0, out=d_out)
+        e0.record()
+        for _ in range(reps):
+            core.warp_resize_frames(d_frames, enc, tables, 0, out=d_out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_pixel = e0.elapsed_time(e1) / reps
+        pixel_kernel = "warp_fused_kernel (+ resize_table_kernel, 3 us): warp + crop + resize of one launch's frames"
+    else:
+        ms_pixel = stage_ms[stage_names[1]]
+        pixel_kernel = "warp_fast_kernel (timed with its preparation kernels)"
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(reps):
+        core.stabilized_displacements(u_d, homs_d, args.definition)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_jac = e0.elapsed_time(e1) / reps
+    Ft = int(u_d.shape[0])
+    jac_bytes = 32.0 * V * Ft + 72.0 * Ft
+    jac_flop = float(args.iters) * V * Ft * 2 * (2 * (2 * args.radius + 1) + 3)
 
     # ---- end-to-end timing: host buffers in, host buffers out ------------------------------------------
     streamed = StreamedCore(core, chunk_frames=args.chunk)
@@ -314,44 +445,37 @@ def run_b200(args):
 
     for _ in range(max(1, args.warmup - 1)):
         e2e_step()
-    barrier()
+    barrier(world)
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
     e1.record()
-    barrier()
+    barrier(world)
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e = max_over_ranks([ms_total, ms_e2e], world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    frames_per_step = F_total
-    value = frames_per_step * args.steps / (ms_total / 1e3)
-    e2e_value = frames_per_step * args.steps / (ms_e2e / 1e3)
+    value = F_total * args.steps / (ms_total / 1e3)
+    e2e_value = F_total * args.steps / (ms_e2e / 1e3)
     h2d = int(h_frames.numel() + sum(v.numel() * v.element_size() for v in h_tracks.values()))
     d2h = int(h_out.numel() + 8)
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    warp_bytes = 6.0 * H * W * F                       # read source once + write stabilized once, per launch
-    achieved = warp_bytes / (stage_ms["warp"] / 1e3) / 1e9
+    peak, peak_src = hbm_peak()
+    pixel_bytes = 6.0 * H * W * F                      # read every source frame once + write every final frame once
+    achieved = pixel_bytes / (ms_pixel / 1e3) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "warp_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = tj["dram_bytes_per_1080p_frame"] * F * (W * H) / (1920.0 * 1080.0)
-        traffic_src = tj["source"]
-    resize_gbs = warp_bytes / (stage_ms["crop_resize"] / 1e3) / 1e9 if "crop_resize" in stage_ms else None
+        key = "fused_dram_bytes_per_1080p_frame" if fused else "dram_bytes_per_1080p_frame"
+        if key in tj:
+            traffic = tj[key] * F * (W * H) / (1920.0 * 1080.0)
+            traffic_src = tj.get("fused_source" if fused else "source")
     out = {
         "metric": "stabilized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -360,29 +484,326 @@ def run_b200(args):
         "config": {"workload": workload_name(args), "frames_per_gpu": F, "tracks": args.tracks,
                    "features_per_pair": int(np.diff(packed["pair_start"]).mean()),
                    "l2": "inputs larger than L2 (1.87 GB of frames per step per GPU)",
-                   "crop": list(crop), "parallelism": f"frames x{world}, Jacobi vertices x{world}"},
+                   "crop": list(crop), "pixel_path": "fused" if fused else "two-kernel",
+                   "parallelism": f"frames x{world}, Jacobi vertices x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         # kernels of this library per step: feature_prepare_masks, pair_sort, row_select, median3x3, prefix,
-        # jacobi_coeff, jacobi_solve, cell_setup, tile_sort, cell_spans, row_segments, warp_fast, crop_combine,
-        # resize_table, crop_resize_rows, stability
-        "gpu_launches": 16 * args.steps,
+        # jacobi_coeff, jacobi_solve, cell_setup, tile_sort, cell_spans, row_segments, crop_edges, crop_combine,
+        # resize_table, warp_fused, stability   (two-kernel path: warp_fast + crop_resize_rows instead of warp_fused)
+        "gpu_launches": (16 if fused else 17) * args.steps,
         "stages_ms": stage_ms,
-        "roofline": {"kernel": "warp_fast_kernel (timed: the whole mf_warp_frames stage = cell_setup + tile_sort + "
-                               "row_segments + warp_fast)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read + dram__bytes_write of the stage's kernels from one ncu --set full capture
+        "roofline": {"kernel": pixel_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "kernel_ms_per_launch": ms_pixel,
+                     # dram__bytes_read + dram__bytes_write of the kernel from one ncu --set full capture
                      # (profiles/warp_traffic.json names it), per 1080p frame, scaled to this launch
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": warp_bytes},
-        "crop_resize_gbs": resize_gbs,
+                     "algorithmic_bytes_per_launch": pixel_bytes},
+        "jacobi": {"ms": ms_jac, "gbs": jac_bytes / (ms_jac / 1e3) / 1e9, "tflops_f64": jac_flop / (ms_jac / 1e3) / 1e12,
+                   "algorithmic_bytes": jac_bytes, "flop": jac_flop, "frames": Ft, "vertices": V,
+                   "note": "HBM is touched twice (load b, store x): the solve is bound by shared memory and the float64 pipe"},
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        fps, detail = cpu_hot_path_fps(args, frames, packed)
-        out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": detail["cores"], "kind": "port",
-                               "sample": detail["sample"], "detail": detail}
+    if world == 1:
+        if not args.no_parity:
+            out["parity_checked"], out["parity"] = parity_self_check(args, core, frames, packed, d_frames, d_out, kept)
+        if not args.no_cpu_baseline:
+            arm = CpuArm(args)
+            fps, wall, detail = arm.sample(frames, packed, warp_frames=2, vm_pairs=16)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": detail["cores"], "kind": detail["kind"],
+                                   "sample": detail["sample"], "wall_s": wall, "detail": detail}
+        if not args.no_api:
+            out["e2e_api"] = api_wall_time(args, frames, local)
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def parity_self_check(args, core, frames, packed, d_frames, d_out, kept):
+    """Outside the timed region: the timed workload's own outputs against the other implementations."""
+    import torch
+    from oracle import reference_port as port
+    F = len(frames)
+    u_d, s_d, enc = kept["u"], kept["s"], kept["enc"]
+    report = {}
+    # (1) production pixel kernel == generic pixel kernel (float32 maps route); timed output == generic kernel
+    #     followed by the stand-alone crop/resize; crop edges of prepare == generic kernel's -- every frame
+    crop_gen = []
+    diff_fast = diff_out = 0
+    for f0 in range(0, F, 20):
+        n = min(20, F - f0)
+        gen, cg, _ = core.warp_frames(d_frames[f0:f0 + n], u_d[f0:f0 + n], s_d[f0:f0 + n], return_maps=True)
+        fast, cf = core.warp_frames(d_frames[f0:f0 + n], u_d[f0:f0 + n], s_d[f0:f0 + n])
+        diff_fast += int((gen != fast).any(dim=3).sum().item()) + int((cg != cf).sum().item())
+        two = core.crop_resize_device(gen, enc)
+        diff_out += int((two != d_out[f0:f0 + n]).any(dim=3).sum().item())
+        crop_gen.append(cg)
+        del gen, fast, two
+    crop_gen = torch.cat(crop_gen)
+    report["fast_vs_generic_kernel_px"] = diff_fast
+    report["timed_output_vs_generic_then_resize_px"] = diff_out
+    report["crop_edges_prepare_vs_generic"] = int((crop_gen != kept["crop_pf"]).sum().item())
+    ok = diff_fast == 0 and diff_out == 0 and report["crop_edges_prepare_vs_generic"] == 0
+    # (2) CPU leg (oracle port: the reference's own OpenCV / NumPy calls) fed with the GPU's paths: 2 frames,
+    #     vertex motion of 4 pairs
+    u = u_d.cpu().numpy(); s = s_d.cpu().numpy()
+    p = port.Params(mesh_row_count=args.mesh, mesh_col_count=args.mesh,
+                    temporal_smoothing_radius=args.radius, optimization_num_iterations=args.iters)
+    idx = [0, F // 2]
+    stab_cpu, _ = port.warp_frames_and_crop(p, [frames[i] for i in idx], u[idx], s[idx])
+    crop = core.decode_crop(enc)
+    cropped_cpu = port.crop_frames(stab_cpu, crop)
+    got = d_out[idx].cpu().numpy()
+    report["cpu_port_vs_gpu_px"] = int(sum((a != b).any(axis=2).sum() for a, b in zip(cropped_cpu, got)))
+    vels = []
+    for i in range(4):
+        e, l, hom = CpuArm.matches_of_pair(packed, i)
+        vels.append(port.vertex_velocities_from_matches(p, args.width, args.height, e, l, hom))
+    u_cpu = np.cumsum(np.concatenate([np.zeros((1,) + vels[0].shape), np.stack(vels).astype(np.float64)]), axis=0)
+    report["u_first_pairs_equal_cpu_port"] = bool(np.array_equal(u_cpu, u[:5]))
+    report["frames_compared"] = F
+    report["crop"] = list(crop)
+    ok = ok and report["cpu_port_vs_gpu_px"] == 0 and report["u_first_pairs_equal_cpu_port"]
+    return bool(ok), report
+
+
+def api_wall_time(args, frames, local):
+    """Wall clock of the drop-in API on the same frames: host tracking, staging, GPU, metric tracking."""
+    import torch
+    from meshflow_b200 import MeshFlowStabilizer
+    st = MeshFlowStabilizer(mesh_row_count=args.mesh, mesh_col_count=args.mesh, temporal_smoothing_radius=args.radius,
+                            optimization_num_iterations=args.iters, device=f"cuda:{local}", chunk_frames=args.chunk)
+    walls, timings = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = st.stabilize_frames(frames, args.definition, reuse_output=True)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+        timings.append({k: round(v, 4) for k, v in r["timings"].items()})
+    F = len(frames)
+    return {"value": F / min(walls), "unit": "frames/s", "call": "MeshFlowStabilizer.stabilize_frames(frames) "
+            "(host FAST/LK/RANSAC on the thread pool, staging, GPU passes, metric tracking)",
+            "wall_s_per_call": [round(w, 3) for w in walls], "first_call_fps": F / walls[0], "cores": os.cpu_count(),
+            "stage_wall_s": timings[-1],
+            "round1_same_box": "scripts/e2e_api.py --impl r01: 9.65 s first call, 7.62 s later (profiles/r02_e2e_api.md)",
+            "tuple": [float(r["cropping_ratio"]), float(r["distortion_score"]), float(r["stability_score"])]}
+
+
+# ------------------------------------------------------------------------------------------------
+# c3: 4K x 1000 frames, frame-sharded (strong scaling), streamed host -> host
+# ------------------------------------------------------------------------------------------------
+class CycledFrames:
+    """F frames backed by a ring of ``ring`` distinct pinned frames (frame i lives in slot i % ring): bounds host
+    memory at 4K x 1000 frames (24.9 GB per copy).  Only contiguous chunk slices that do not wrap are served."""
+
+    def __init__(self, ring_tensor, frames):
+        self.t, self.n = ring_tensor, int(frames)
+        self.shape = (self.n,) + tuple(ring_tensor.shape[1:])
+
+    def __getitem__(self, sl):
+        a, b = sl.start or 0, sl.stop
+        ring = self.t.shape[0]
+        a0 = a % ring
+        if a0 + (b - a) > ring:
+            raise IndexError("chunk wraps around the frame ring")
+        return self.t[a0:a0 + (b - a)]
+
+
+def run_c3(args):
+    import torch
+    import torch.distributed as dist
+    from meshflow_b200 import DeviceCore, MeshSpec, StreamedCore, distributed as mfd, workloads
+
+    world, rank, local = dist_setup()
+    dev = torch.device("cuda", local)
+    W, H, Ftot = args.width, args.height, args.frames
+    plan = mfd.ShardPlan.even(Ftot) if world > 1 else None
+    F = plan.local_frames if plan else Ftot
+    first = plan.first_frame if plan else 0
+    core = DeviceCore(MeshSpec(W, H, args.mesh, args.mesh), device=dev, radius=args.radius, iterations=args.iters)
+    rng = np.random.default_rng(4321)
+    ring = 4 * args.chunk
+    canvas = workloads.textured_video(np.random.default_rng(4321 + rank), ring, W, H)
+    h_ring = torch.empty((ring, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    for i, f in enumerate(canvas):
+        h_ring[i] = torch.from_numpy(f)
+    h_out_ring = torch.empty((ring, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    # tracks of the WHOLE video from one seed (every rank generates the same and keeps its own pairs)
+    tr = workloads.synthetic_tracks(rng, Ftot, 6000, W, H)
+    npairs = plan.pairs_needed() if plan else Ftot - 1
+    a, b = tr["pair_start"][first], tr["pair_start"][first + npairs]
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    tracks = dict(early=pin(tr["early"][a:b]), late=pin(tr["late"][a:b]), offset=pin(tr["offset"][a:b]), keep=pin(tr["keep"][a:b]),
+                  pair_start=pin((tr["pair_start"][first:first + npairs + 1] - a).astype(np.int32)),
+                  homographies=pin(tr["homographies"][first:first + npairs].reshape(-1, 9)))
+    streamed = StreamedCore(core, chunk_frames=args.chunk)
+    h_in, h_out = CycledFrames(h_ring, F), CycledFrames(h_out_ring, F)
+
+    def step():
+        enc, u, s = streamed.run(h_in, tracks, h_out, args.definition, plan=plan)
+        return enc, core.stability_score(s).item()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(args.warmup):
+        enc, _ = step()
+    barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        enc, score = step()
+    e1.record()
+    barrier(world)
+    clocks = sampler.stop()
+    (ms,) = max_over_ranks([e0.elapsed_time(e1)], world, dev)
+    if rank == 0:
+        fps = Ftot * args.steps / (ms / 1e3)
+        bytes_step = 2.0 * 3 * H * W * Ftot
+        print(json.dumps({
+            "metric": "stabilized frames/sec (4K, host frames in -> host frames out)", "value": fps, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64/u8", "data": "synthetic",
+            "config": {"workload": f"synthetic 4K {Ftot}-frame video, {args.mesh}x{args.mesh} mesh, CONSTANT_HIGH weights, "
+                                   f"frame-sharded over {world} GPU(s) (BASELINE.json configs[2])",
+                       "frames_per_gpu": F, "tracks": "synthetic, 6000 per pair", "chunk_frames": args.chunk,
+                       "host_frames": f"{ring} distinct pinned frames per rank, cycled (bounds host memory; every chunk is "
+                                      f"a real H2D + D2H of {args.chunk} x {3 * H * W / 1e6:.1f} MB)",
+                       "crop": list(core.decode_crop(enc)), "stability_score": score},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": int(3 * H * W * Ftot), "d2h_bytes_per_step": int(3 * H * W * Ftot)},
+            "pcie_gbs_per_direction_aggregate": bytes_step / 2 / (ms / args.steps / 1e3) / 1e9,
+            "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# c4: Jacobi only, vertex-sharded (strong scaling)
+# ------------------------------------------------------------------------------------------------
+def run_c4(args):
+    import torch
+    import torch.distributed as dist
+    from meshflow_b200 import DeviceCore, MeshSpec, distributed as mfd
+
+    world, rank, local = dist_setup()
+    dev = torch.device("cuda", local)
+    F, R = args.frames, args.mesh
+    core = DeviceCore(MeshSpec(args.width, args.height, R, R), device=dev, radius=args.radius, iterations=args.iters)
+    V = core.mesh.vertices
+    g = torch.Generator(device=dev).manual_seed(7)
+    u = torch.cumsum(torch.randn((F, V, 2), generator=g, device=dev, dtype=torch.float64) * 3.0, dim=0).view(F, R + 1, R + 1, 2).contiguous()
+    rng = np.random.default_rng(7)
+    homs = np.tile(np.eye(3), (F, 1, 1))
+    homs[:, :2, :2] += rng.normal(0, 0.01, (F, 2, 2))
+    homs[:, :2, 2] = rng.normal(0, 8.0, (F, 2))
+    homs[-1] = np.eye(3)
+    hd = torch.from_numpy(homs).to(dev)
+    v0, v1, _ = mfd.vertex_shard(V, world, rank)
+    s = torch.empty_like(u)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    results = {}
+    for definition in (args.definition, 2):
+        def step(gather):
+            core.stabilized_displacements(u, hd, definition, vertex_range=(v0, v1), out=s)
+            return mfd.gather_paths(s.view(F, V, 2), V) if gather and world > 1 else s
+        for _ in range(args.warmup):
+            step(True)
+        barrier(world)
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        for _ in range(args.steps):
+            step(False)
+        e1.record()
+        for _ in range(args.steps):
+            step(True)
+        e2.record()
+        barrier(world)
+        ms_solve, ms_with_gather = max_over_ranks([e0.elapsed_time(e1) / args.steps, e1.elapsed_time(e2) / args.steps], world, dev)
+        results[definition] = (ms_solve, ms_with_gather)
+    if rank == 0:
+        flop = float(args.iters) * V * F * 2 * (2 * (2 * args.radius + 1) + 3)
+        byts = 32.0 * V * F + 72.0 * F
+        ms_solve, ms_g = results[args.definition]
+        print(json.dumps({
+            "metric": "Jacobi path optimisation, float64 TFLOP/s", "value": flop / (ms_solve / 1e3) / 1e12, "unit": "TFLOP/s (f64)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_solve,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Jacobi-only stress: {R}x{R} mesh ({V} vertices) x {F} frames, radius {args.radius}, "
+                                   f"{args.iters} iterations, vertex-sharded over {world} GPU(s) (BASELINE.json configs[3])",
+                       "definition": args.definition},
+            "solve_ms": ms_solve, "solve_plus_all_gather_ms": ms_g, "hbm_gbs": byts / (ms_solve / 1e3) / 1e9,
+            "algorithmic_bytes": byts, "flop": flop,
+            "constant_high_solve_ms": results[2][0],
+            "note": "vector float64 peak of a B200 is ~37 TFLOP/s (148 SMs x 64 FMA/clk x 2 x 1.965 GHz); the solve keeps a "
+                    "trajectory on chip and touches HBM twice"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# c5: warp-only sweep, every rank its own frames (weak scaling)
+# ------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    from meshflow_b200 import DeviceCore, MeshSpec
+
+    world, rank, local = dist_setup()
+    dev = torch.device("cuda", local)
+    peak, peak_src = hbm_peak()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    points = []
+    for (W, H, nf) in [(1280, 720, 64), (1920, 1080, 64), (2560, 1440, 64), (3840, 2160, 32), (7680, 4320, 8)]:
+        for R in (16, 64):
+            rng = np.random.default_rng(99 + rank)
+            core = DeviceCore(MeshSpec(W, H, R, R), device=dev)
+            frames = torch.randint(0, 256, (nf, H, W, 3), dtype=torch.uint8, device=dev)
+            u = np.cumsum(rng.normal(0, 2.0, (nf, R + 1, R + 1, 2)), axis=0)
+            amp = 2.5 * min(1.0, (W / R) / 120.0)            # keep the mesh un-folded on small cells
+            s = u + rng.normal(0, amp, u.shape) + rng.normal(0, 3.0, (nf, 1, 1, 2))
+            ud, sd = torch.from_numpy(u).to(dev), torch.from_numpy(s).to(dev)
+            out = torch.empty_like(frames)
+
+            def warp():
+                return core.warp_frames(frames, ud, sd, out=out)
+
+            def fused_pass(enc):
+                _, tables = core.warp_prepare(ud, sd)
+                return core.warp_resize_frames(frames, enc, tables, 0, out=out)
+
+            _, crop = warp()
+            enc = core.combine_crop(crop)
+            for _ in range(max(1, args.warmup - 1)):
+                warp(); fused_pass(enc)
+            barrier(world)
+            e = [ev() for _ in range(3)]
+            e[0].record()
+            for _ in range(args.steps):
+                warp()
+            e[1].record()
+            for _ in range(args.steps):
+                fused_pass(enc)
+            e[2].record()
+            barrier(world)
+            tw, tf = max_over_ranks([e[0].elapsed_time(e[1]) / args.steps / nf, e[1].elapsed_time(e[2]) / args.steps / nf], world, dev)
+            gb = 6.0 * H * W / 1e9
+            points.append({"size": [W, H], "mesh": R, "frames_per_gpu": nf,
+                           "warp_us_per_frame": tw * 1e3, "warp_frames_per_s": world / (tw / 1e3), "warp_gbs_per_gpu": gb / (tw / 1e3),
+                           "warp_frac_of_hbm_peak": gb / (tw / 1e3) / peak,
+                           "fused_warp_crop_resize_us_per_frame": tf * 1e3, "fused_frames_per_s": world / (tf / 1e3),
+                           "fused_frac_of_hbm_peak": gb / (tf / 1e3) / peak, "crop": list(core.decode_crop(enc))})
+            del frames, out
+            torch.cuda.empty_cache()
+    if rank == 0:
+        p1080 = [p for p in points if p["size"] == [1920, 1080] and p["mesh"] == 16][0]
+        print(json.dumps({
+            "metric": "warp-only frames/sec (1080p, 16x16 cell homographies)", "value": p1080["warp_frames_per_s"], "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": p1080["warp_us_per_frame"] * 64 / 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "warp-only throughput sweep 720p -> 8K with 16x16 and 64x64 mesh-cell homographies "
+                                   "(BASELINE.json configs[4]); per-vertex-noise meshes (rougher than a stabilizer's output)",
+                       "warp": "mf_warp_frames (prepare + stabilized frames to HBM)",
+                       "fused": "mf_warp_prepare + mf_warp_resize_frames (final frames only)"},
+            "peak": peak, "peak_source": peak_src, "sweep": points}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -392,7 +813,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        {"c2": run_c2, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
 
 
 if __name__ == "__main__":
