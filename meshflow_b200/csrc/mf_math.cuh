@@ -264,10 +264,17 @@ struct alignas(16) Cell {
 
 // rest: 4 corners TL,TR,BL,BR of the rest cell (integer valued), stab: the stabilized corners already
 // rounded to float32 (cv2.findHomography converts its input to float32).
+MF_HD void cell_setup_from_homographies(const double* rest, const double* Hus, const double* Hsu, int W, int H, Cell& out);
+
 MF_HD void cell_setup(const double* rest, const double* stab, int W, int H, Cell& out) {
   double Hus[9], Hsu[9];
   homography_4pt(rest, stab, Hus);
   homography_4pt(stab, rest, Hsu);
+  cell_setup_from_homographies(rest, Hus, Hsu, W, H, out);
+}
+
+// Everything of cell_setup after the two 4-point solves (the device solves them with eight lanes per system).
+MF_HD void cell_setup_from_homographies(const double* rest, const double* Hus, const double* Hsu, int W, int H, Cell& out) {
   for (int i = 0; i < 8; ++i) out.Hsu[i] = Hsu[i];
   inverse3x3(Hus, out.Mi);
   double minx = rest[0], maxx = rest[0], miny = rest[1], maxy = rest[1];

@@ -45,39 +45,120 @@ static constexpr int kFastRows = MF_FAST_ROWS;     // fast path: rows per warp (
 static constexpr int kFastTileH = 8 * kFastRows;   // 120: divides 720, 1080, 1440, 2160, 4320
 static_assert(kFastRows >= 1 && kFastRows <= 16, "four mask bits per row in one 64-bit word, four row bits per queue entry");
 
-__global__ void __launch_bounds__(128) cell_setup_kernel(
+// Exact 4-point homography (mf_math.cuh homography_4pt: 8x8 Gaussian elimination with partial pivoting, fixed
+// operation order) with EIGHT lanes per system, one matrix row each: pivot search and row exchange by shuffles, every
+// lane eliminates its own row.  Same operations on the same operands as the sequential routine, so the result is
+// bit-identical; the sequential version kept the 8x9 matrix in local memory behind a data-dependent pivot index and
+// ran at 6 % occupancy.  Returns h[0..7] (h22 = 1) in every lane of the group.
+__device__ __forceinline__ double shfl8(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
 
+// (x, y) -> (X, Y): the correspondence of THIS lane's corner (corner = r >> 1).
+__device__ __forceinline__ void homography_4pt_rows(double x, double y, double X, double Y, int r, double (&h)[8]) {
+  double a[9];
+  {
+    const double D = (r & 1) ? Y : X;
+    const bool odd = (r & 1) != 0;
+    a[0] = odd ? 0.0 : x; a[1] = odd ? 0.0 : y; a[2] = odd ? 0.0 : 1.0;
+    a[3] = odd ? x : 0.0; a[4] = odd ? y : 0.0; a[5] = odd ? 1.0 : 0.0;
+    a[6] = -MF_MUL(x, D); a[7] = -MF_MUL(y, D); a[8] = D;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // partial pivoting: the FIRST row >= k with the largest |a[k]| (strict comparison in the sequential routine)
+    double best = r >= k ? fabs(a[k]) : -1.0;
+    int piv = r;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, m, 8);
+      const int op = __shfl_xor_sync(0xffffffffu, piv, m, 8);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    double p[9];
+#pragma unroll
+    for (int j = k; j < 9; ++j) {
+      const double from_piv = shfl8(a[j], piv), from_k = shfl8(a[j], k);
+      p[j] = from_piv;                                       // the pivot row, known to every lane
+      if (r == k) a[j] = from_piv; else if (r == piv) a[j] = from_k;
+    }
+    if (r > k) {
+      const double f = MF_DIV(a[k], p[k]);
+#pragma unroll
+      for (int j = k; j < 9; ++j) a[j] = MF_SUB(a[j], MF_MUL(f, p[j]));
+    }
+  }
+#pragma unroll
+  for (int i = 7; i >= 0; --i) {
+    double acc = a[8];
+#pragma unroll
+    for (int j = i + 1; j < 8; ++j) acc = MF_SUB(acc, MF_MUL(a[j], h[j]));
+    h[i] = shfl8(MF_DIV(acc, a[i]), i);                      // row i's lane holds the valid value
+  }
+}
+
+// Sixteen lanes per cell: lanes 0-7 solve the unstabilized -> stabilized homography, lanes 8-15 the inverse
+// direction (a separate solve, mfs.py:1041-1042).  homs[cell] = Hus[0..7], Hsu[0..7].
+__global__ void __launch_bounds__(128) cell_homographies_kernel(
     const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
-    int nf, int W, int H, int R, int C, int tiles_x, int tiles_y, Cell* __restrict__ cells,
+    int nf, int R, int C, double* __restrict__ homs) {
+  const int ncell = R * C;
+  const int64_t total = (int64_t)nf * ncell;
+  const int sub = threadIdx.x & 15;
+  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const bool valid = idx < total;
+  if (!valid) idx = total - 1;                               // keep the shuffles of the warp complete
+  const int f = (int)(idx / ncell), id = (int)(idx - (int64_t)f * ncell);
+  const int r = id / C, c = id - r * C;
+  const int V = (R + 1) * (C + 1);
+  // this lane's matrix row belongs to corner (row & 7) >> 1 of the cell (TL, TR, BL, BR): only that vertex is read
+  const int row = sub & 7, corner = row >> 1;
+  const int v = (r + (corner >> 1)) * (C + 1) + c + (corner & 1);
+  const size_t o = ((size_t)f * V + v) * 2;
+  const double rx = (double)vertex_xy[2 * v], ry = (double)vertex_xy[2 * v + 1];
+  // stabilized vertex = rest + (s - u), float64, then rounded to float32 by cv2.findHomography (mfs.py:964-967, 1025)
+  const double sx = (double)(float)MF_ADD(rx, MF_SUB(s[o], u[o])), sy = (double)(float)MF_ADD(ry, MF_SUB(s[o + 1], u[o + 1]));
+  const bool inverse = sub >= 8;
+  double h[8];
+  homography_4pt_rows(inverse ? sx : rx, inverse ? sy : ry, inverse ? rx : sx, inverse ? ry : sy, row, h);
+  double mine = h[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mine = (sub & 7) == i ? h[i] : mine;
+  if (valid) homs[idx * 16 + sub] = mine;
+}
+
+// One thread per (frame, cell): the rest of the set-up from the two homographies (adjugate inverse, bounds, support
+// box, float32 forms, membership half-planes); the thread then files the cell into the candidate list of every
+// 128 x 8 output tile its box touches.
+__global__ void __launch_bounds__(128) cell_setup_kernel(
+    const double* __restrict__ u, const double* __restrict__ s, const float* __restrict__ vertex_xy,
+    const double* __restrict__ homs, int nf, int W, int H, int R, int C, int tiles_x, int tiles_y, Cell* __restrict__ cells,
     CellFast* __restrict__ fast, CellSpan* __restrict__ spans,
-    int* __restrict__ tile_count, uint16_t* __restrict__ tile_list, int32_t* __restrict__ crop_out,
-    int* __restrict__ edge_count, uint16_t* __restrict__ edge_tiles) {
+    int* __restrict__ tile_count, uint16_t* __restrict__ tile_list, int32_t* __restrict__ crop_out) {
   const int ncell = R * C;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)nf * ncell) return;
   const int f = (int)(idx / ncell), id = (int)(idx - (int64_t)f * ncell);
   const int r = id / C, c = id - r * C;
-  const int V = (R + 1) * (C + 1);
   if (id == 0 && crop_out) {  // identities of the max/max/min/min edge searches (mfs.py:992-995)
     crop_out[4 * f + 0] = 0; crop_out[4 * f + 1] = 0;
     crop_out[4 * f + 2] = W - 1; crop_out[4 * f + 3] = H - 1;
   }
-  double rest[8], stab[8];
+  double rest[8];
   const int vidx[4] = {r * (C + 1) + c, r * (C + 1) + c + 1, (r + 1) * (C + 1) + c, (r + 1) * (C + 1) + c + 1};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int v = vidx[k];
-    const size_t o = ((size_t)f * V + v) * 2;
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const double rv = (double)vertex_xy[2 * v + d];
-      rest[2 * k + d] = rv;
-      // stabilized vertex = rest + (s - u), float64, then rounded to float32 by cv2.findHomography
-      stab[2 * k + d] = (double)(float)MF_ADD(rv, MF_SUB(s[o + d], u[o + d]));   // mfs.py:964-967, 1025
-    }
+    rest[2 * k] = (double)vertex_xy[2 * vidx[k]];
+    rest[2 * k + 1] = (double)vertex_xy[2 * vidx[k] + 1];
   }
+  double Hus[9], Hsu[9];
+  const double2* hp = reinterpret_cast<const double2*>(homs + idx * 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 a = __ldg(hp + i), b = __ldg(hp + 4 + i);
+    Hus[2 * i] = a.x; Hus[2 * i + 1] = a.y; Hsu[2 * i] = b.x; Hsu[2 * i + 1] = b.y;
+  }
+  Hus[8] = 1.0; Hsu[8] = 1.0;
   Cell cell;
-  cell_setup(rest, stab, W, H, cell);
+  cell_setup_from_homographies(rest, Hus, Hsu, W, H, cell);
   if (fast != nullptr) {                  // fast path: box-local float32 map + membership half-planes
     CellFast cf;
     CellSpan sp;
@@ -93,18 +174,26 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
   // Tiles that hold a border cell are tagged: only their rows take part in the crop-edge searches.
   const bool edge_cell = (cell.edge_flags & kEdgeAny) != 0u;
   const int ntiles = tiles_x * tiles_y;
-  const int tx0 = cell.bx0 / kTileW, tx1 = cell.bx1 / kTileW;
-  const int ty0 = cell.by0 / kTileH, ty1 = cell.by1 / kTileH;
-  for (int ty = ty0; ty <= ty1; ++ty) {
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      const size_t t = (size_t)f * ntiles + (size_t)ty * tiles_x + tx;
-      const int slot = atomicAdd(&tile_count[t], 1) & kCountMask;
-      if (slot < kTileCap) tile_list[t * kTileCap + slot] = (uint16_t)id;
-      if (edge_cell) {
-        // the first border cell to tag a tile also lists it: crop_edges_kernel only visits listed tiles
-        const int old = atomicOr(&tile_count[t], kEdgeFlag);
-        if (!(old & kEdgeFlag) && edge_count != nullptr) edge_tiles[(size_t)f * ntiles + atomicAdd(&edge_count[f], 1)] = (uint16_t)(ty * tiles_x + tx);
-      }
+  const int tx0 = cell.bx0 / kTileW, ty0 = cell.by0 / kTileH;
+  const int ntx = cell.bx1 / kTileW - tx0 + 1, n = ntx * (cell.by1 / kTileH - ty0 + 1);
+  const size_t tbase = (size_t)f * ntiles;
+  const int flag = edge_cell ? kEdgeFlag : 0;               // carried by the same atomic as the count
+  // four tiles per step: the atomics of a step are independent, so their round trips to L2 overlap
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    size_t t[4];
+    int slot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = min(k0 + j, n - 1);
+      t[j] = tbase + (size_t)(ty0 + k / ntx) * tiles_x + (tx0 + k % ntx);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) slot[j] = k0 + j < n ? (atomicAdd(&tile_count[t[j]], 1) & kCountMask) : kTileCap;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (k0 + j >= n) continue;
+      if (slot[j] < kTileCap) tile_list[t[j] * kTileCap + slot[j]] = (uint16_t)id;
+      if (flag) atomicOr(&tile_count[t[j]], flag);          // no return value needed: tile_sort_kernel lists the tagged tiles
     }
   }
 }
@@ -113,10 +202,16 @@ __global__ void __launch_bounds__(128) cell_setup_kernel(
 // descending cell id ("the last cell written wins", mfs.py:1060-1061).  Lists are short (typically
 // 4-8 ids): one thread sorts one list in place.
 __global__ void __launch_bounds__(128) tile_sort_kernel(const int* __restrict__ tile_count,
-                                                        uint16_t* __restrict__ tile_list, int64_t ntiles) {
+                                                        uint16_t* __restrict__ tile_list, int64_t ntiles_total, int ntiles,
+                                                        int* __restrict__ edge_count, uint16_t* __restrict__ edge_tiles) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntiles) return;
-  const int n = tile_count[t] & kCountMask;
+  if (t >= ntiles_total) return;
+  const int craw = tile_count[t];
+  if ((craw & kEdgeFlag) && edge_count != nullptr) {        // tiles that hold a border cell: crop_edges_kernel's work list
+    const int f = (int)(t / ntiles);
+    edge_tiles[(size_t)f * ntiles + atomicAdd(&edge_count[f], 1)] = (uint16_t)(t - (int64_t)f * ntiles);
+  }
+  const int n = craw & kCountMask;
   if (n < 2 || n > kTileCap) return;
   uint16_t* l = tile_list + t * kTileCap;
   for (int i = 1; i < n; ++i) {
@@ -596,6 +691,7 @@ struct WarpWorkspace {
   uint32_t* rowseg;
   uint4* lane_owner;     // [nf][H][tiles_x] x 32 uint16: owner of each lane's group of four pixels
   uint32_t* span_tab;    // [nf][R*C][span_rows]: member interval of a cell on each row of its box
+  double* homs;          // [nf][R*C][16]: the two 4-point homographies of every cell (Hus, Hsu)
   int* edge_count;       // [nf]: tiles of the frame that hold a border cell
   uint16_t* edge_tiles;  // [nf][tiles]: their indices (order of arrival)
   int span_rows;
@@ -622,6 +718,7 @@ static bool carve_warp(Carver& cv, int nf, int W, int H, int R, int C, WarpWorks
   w.lane_owner = cv.take<uint4>((size_t)nf * H * tiles_x * 4);
   w.span_rows = span_rows_for(H, R);
   w.span_tab = cv.take<uint32_t>((size_t)nf * R * C * w.span_rows);
+  w.homs = cv.take<double>((size_t)nf * R * C * 16);
   w.edge_count = cv.take<int>((size_t)nf);
   w.edge_tiles = cv.take<uint16_t>((size_t)nf * tiles);
   return cv.ok();
@@ -664,12 +761,15 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
   if (ce == cudaSuccess) ce = cudaMemsetAsync(w.edge_count, 0, (size_t)nf * sizeof(int), st);
   if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "warp: memset: %s", cudaGetErrorString(ce));
   const int64_t ncells = (int64_t)nf * R * C;
+  mf::cell_homographies_kernel<<<(unsigned)((ncells * 16 + 127) / 128), 128, 0, st>>>(u, s, vertex_xy, nf, R, C, w.homs);
+  if (int e = mf::check_launch("cell_homographies")) return e;
   mf::cell_setup_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(
-      u, s, vertex_xy, nf, W, H, R, C, tiles_x, tiles_y, w.cells, fast ? w.fast : nullptr, fast ? w.spans : nullptr,
-      w.tile_count, w.tile_list, crop_out, w.edge_count, w.edge_tiles);
+      u, s, vertex_xy, w.homs, nf, W, H, R, C, tiles_x, tiles_y, w.cells, fast ? w.fast : nullptr, fast ? w.spans : nullptr,
+      w.tile_count, w.tile_list, crop_out);
   if (int e = mf::check_launch("cell_setup")) return e;
   const int64_t ntiles = (int64_t)nf * tiles_x * tiles_y;
-  mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles);
+  mf::tile_sort_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(w.tile_count, w.tile_list, ntiles, tiles_x * tiles_y,
+                                                                       w.edge_count, w.edge_tiles);
   if (int e = mf::check_launch("tile_sort")) return e;
   if (fast) {
     const int64_t nspan = ncells * ((w.span_rows + mf::kSpanRowsPerThread - 1) / mf::kSpanRowsPerThread);

@@ -211,13 +211,15 @@ __global__ void __launch_bounds__(128) crop_edges_kernel(
   const int craw = __ldg(tile_count + tile);
   const int x0 = tx * kTileW, x1 = min(W - 1, x0 + kTileW - 1);
   const uint32_t* rs = rowseg + (((size_t)f * H + y) * tiles_x + tx) * segcap;
-  unsigned seg[kSegMax];
-  int ns = 0;
-  for (int i = 0; i < segcap; ++i) {
-    const unsigned v = __ldg(rs + i);
-    if (v == kSegSentinel) break;
-    seg[ns++] = v;
+  unsigned seg[kSegMax];                                     // the whole list in independent 16-byte loads (segcap is 8 or 16)
+#pragma unroll
+  for (int i = 0; i < kSegMax / 4; ++i) {
+    const uint4 q = 4 * i < segcap ? __ldg(reinterpret_cast<const uint4*>(rs) + i) : make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
+    seg[4 * i] = q.x; seg[4 * i + 1] = q.y; seg[4 * i + 2] = q.z; seg[4 * i + 3] = q.w;
   }
+  int ns = 0;
+#pragma unroll
+  for (int i = 0; i < kSegMax; ++i) ns += seg[i] != kSegSentinel ? 1 : 0;      // entries are contiguous from the front
   if ((seg[0] & 0xffffu) == kSegIrregular) ns = -1;
   row_crop_edges(cells + (size_t)f * ncell, tile_list + tile * kTileCap, craw & kCountMask, ncell, seg, ns, x0, x1, y, W, H,
                  crop_out + 4 * f);
@@ -399,22 +401,26 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
   const unsigned pitch = (unsigned)W * 3u;
   const bool word_store = kShared || (((sink.pitch & 3u) == 0u) && ((reinterpret_cast<uintptr_t>(sink.at(px0, y_first)) & 3u) == 0u));
   // running pointers: one add per row instead of a 64-bit multiply chain
+  // Every lane loads an owner every row, lanes without pixels from a clamped (valid) entry: a lane-dependent branch
+  // around the load would make the other lanes' path rewrite the load's destination register and stall on it.
   const size_t own_stride = (size_t)T.tiles_x * 32;
-  const uint16_t* own = T.lane_owner + ((size_t)f * H + y_first) * own_stride + (px0 >> 2);
+  const uint16_t* own = T.lane_owner + ((size_t)f * H + y_first) * own_stride + min(px0 >> 2, T.tiles_x * 32 - 1);
   uint8_t* drow = kShared ? nullptr : sink.at(px0, y_first);
   unsigned srow = kShared ? sink_shared + (unsigned)(y_first - sink.oy) * sink.pitch + (unsigned)(px0 - sink.ox) * 3u : 0u;
   const CellFast* ffast = T.fast + fcell0;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // the lists' shared-window addresses, once: generic pointers would be re-derived (S2R + LEA) every row
+  const unsigned med_sh = (unsigned)__cvta_generic_to_shared(q_med), ex_sh = (unsigned)__cvta_generic_to_shared(q_ex);
   int n_med = 0, n_ex = 0;                                   // entries in the warp's two lists (warp-uniform)
 
   // the owner of the next row's group is requested one row ahead (it comes from L2)
   unsigned own_next = kSegNone;
-  if (nrows > 0 && npx > 0) own_next = __ldg(own);
+  if (nrows > 0) own_next = __ldg(own);
 #pragma unroll 1
   for (int r = 0; r < nrows; ++r, own += own_stride, drow += kShared ? 0 : sink.pitch, srow += kShared ? sink.pitch : 0u) {
     const int py = y_first + r;
     const unsigned id = own_next;
-    if (r + 1 < nrows && npx > 0) own_next = __ldg(own + own_stride);
+    if (r + 1 < nrows) own_next = __ldg(own + own_stride);      // warp-uniform condition
     unsigned flag = 0u;                                      // bits 0-3: per-pixel tap fetch, bits 4-7: float64 path
     bool fast_group = false;
     unsigned nu[kPix], nv[kPix];
@@ -512,8 +518,10 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
       const unsigned mm = flag & 15u, xm = flag >> 4;
       const unsigned bal_m = __ballot_sync(0xffffffffu, mm != 0u), bal_x = __ballot_sync(0xffffffffu, xm != 0u);
       const unsigned tag = (unsigned)lane | ((unsigned)r << 5);
-      if (mm != 0u) q_med[n_med + __popc(bal_m & lt_mask)] = (uint16_t)(tag | (mm << 10));
-      if (xm != 0u) q_ex[n_ex + __popc(bal_x & lt_mask)] = (uint16_t)(tag | (xm << 10));
+      if (mm != 0u)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(med_sh + 2u * (unsigned)(n_med + __popc(bal_m & lt_mask))), "h"((unsigned short)(tag | (mm << 10))) : "memory");
+      if (xm != 0u)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(ex_sh + 2u * (unsigned)(n_ex + __popc(bal_x & lt_mask))), "h"((unsigned short)(tag | (xm << 10))) : "memory");
       n_med += __popc(bal_m);
       n_ex += __popc(bal_x);
     }
@@ -668,11 +676,16 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_k
   const int X0 = xa & ~3;
   const uint8_t* src = frames_in + (size_t)fl * H * W * 3;
   const unsigned tile_shared = (unsigned)__cvta_generic_to_shared(sm.tile);
+  // the tile's stabilized rows split evenly over the eight warps (7 or 8 each for a typical 61-64 rows): the warps
+  // meet at a barrier, so the longest share is what counts.  (Per-warp ready flags instead of the barrier -- a warp
+  // only needs the rows of two or three warps -- were measured: 3.73 ms vs 3.60 ms per 300 frames, the polling costs
+  // more issue slots than the barrier wastes.)
+  const int total = yb - ya + 1, base = total >> 3, extra = total & 7;
   {
     PixelSink sink;
     sink.base = sm.tile; sink.pitch = kStabPitch; sink.ox = X0; sink.oy = ya;
-    const int y_first = ya + warp * kStabRowsPerWarp;
-    const int nrows = min(kStabRowsPerWarp, yb - y_first + 1);
+    const int y_first = ya + warp * base + min(warp, extra);
+    const int nrows = base + (warp < extra ? 1 : 0);
 #ifdef MF_EXP_NO_WARP                  // timing experiment only: cost of the resize phase alone
     if (false)
 #else
@@ -754,8 +767,10 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_k
     fused_hsum(tile_shared + (unsigned)(rq - ya) * kStabPitch, woff, shift, wx, Q);
   }
 #endif
+  int4 yt_next = __ldg(ytab + y_out0);
   for (int py = y_out0; py <= y_out1; ++py, drow += out_pitch) {
-    const int4 yt = __ldg(ytab + py);
+    const int4 yt = yt_next;
+    if (py < y_out1) yt_next = __ldg(ytab + py + 1);         // requested a row ahead (warp-uniform condition)
     const int r0 = top + yt.x, r1 = top + yt.y;              // warp-uniform
     const bool flip = swapped ? step(Q, P, rq, rp, r0, r1, yt) : step(P, Q, rp, rq, r0, r1, yt);
     swapped = swapped != flip;
