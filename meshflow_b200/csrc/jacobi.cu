@@ -254,6 +254,76 @@ __global__ void __launch_bounds__(512) jacobi_window_kernel(
   }
 }
 
+// Fallback without a frame limit (videos longer than the on-chip kernels hold: F > 10 240, or a radius whose
+// padded trajectory does not fit shared memory): one launch per sweep, trajectories ping-pong between two global
+// buffers ([F][n] layout, adjacent threads = adjacent systems, so every access is coalesced and the 2 radius + 1
+// neighbours of a frame come from L2).  Same element formula and summation order as the on-chip kernels.
+__global__ void __launch_bounds__(256) jacobi_weights_kernel(int radius, double* __restrict__ w) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > radius) return;
+  const double a = (3.0 / (double)radius) * (double)k;
+  w[k] = exp(-(a * a));
+}
+
+__global__ void __launch_bounds__(256) jacobi_sweep_global_kernel(
+    const double* __restrict__ x_in, int64_t in_stride, int64_t in_col0, const double* __restrict__ b, int64_t n_sys,
+    int64_t sys_begin, double* __restrict__ x_out, int64_t out_stride, int64_t out_col0, int F, int64_t n_cols, int radius,
+    const double* __restrict__ inv_diag, const double* __restrict__ two_lambda, const double* __restrict__ w) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (c >= n_cols) return;
+  double acc = 0.0;
+  const int lo = max(0, t - radius), hi = min(F - 1, t + radius);
+  for (int r = lo; r <= hi; ++r) {
+    const int k = r - t;
+    acc = fma(__ldg(w + (k < 0 ? -k : k)), x_in[(int64_t)r * in_stride + in_col0 + c], acc);
+  }
+  x_out[(int64_t)t * out_stride + out_col0 + c] = inv_diag[t] * fma(two_lambda[t], acc, b[(int64_t)t * n_sys + sys_begin + c]);
+}
+
+__global__ void __launch_bounds__(256) jacobi_copy_kernel(const double* __restrict__ b, int64_t n_sys, int64_t sys_begin,
+                                                          double* __restrict__ out, int F, int64_t n_cols) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_cols) out[(int64_t)blockIdx.y * n_sys + sys_begin + c] = b[(int64_t)blockIdx.y * n_sys + sys_begin + c];
+}
+
+static constexpr int kGlobalMaxRadius = 1023;
+static size_t global_scratch_bytes(int F, int64_t n_sys) {
+  return align_up((size_t)(kGlobalMaxRadius + 1) * sizeof(double), 256) + align_up((size_t)F * (size_t)n_sys * sizeof(double), 256);
+}
+
+// Frames the on-chip kernels hold per solve (jacobi_window_kernel: 20 frames x 512 threads).
+static constexpr int kOnChipMaxFrames = 20 * 512;
+static bool needs_global_path(int F, int radius) {
+  const size_t smem = (size_t)(F + 2 * radius) * sizeof(double2) + (size_t)(2 * radius + 1) * sizeof(double);
+  return F > kOnChipMaxFrames || smem > 227 * 1024;
+}
+
+static int launch_global(const double* u, double* s, int F, int64_t n_sys, int64_t sys_begin, int64_t n_cols, int radius,
+                         int iterations, const double* inv_diag, const double* two_lambda, void* scratch, cudaStream_t st) {
+  if (radius > kGlobalMaxRadius) return fail(MF_E_UNSUPPORTED, "jacobi: radius %d exceeds %d", radius, kGlobalMaxRadius);
+  if (F > 65535) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds 65535 frames per solve", F);
+  double* w = (double*)scratch;
+  double* tmp = (double*)((char*)scratch + align_up((size_t)(kGlobalMaxRadius + 1) * sizeof(double), 256));
+  jacobi_weights_kernel<<<(radius + 256) / 256, 256, 0, st>>>(radius, w);
+  const dim3 grid((unsigned)((n_cols + 255) / 256), (unsigned)F);
+  if (iterations == 0) {
+    jacobi_copy_kernel<<<grid, 256, 0, st>>>(u, n_sys, sys_begin, s, F, n_cols);
+    return check_launch("jacobi_copy");
+  }
+  // sweep i (1-based) writes `s` when (iterations - i) is even, so that the last one lands in `s`
+  const double* in = u; int64_t in_stride = n_sys, in_col0 = sys_begin;
+  for (int i = 1; i <= iterations; ++i) {
+    const bool to_s = ((iterations - i) & 1) == 0;
+    double* out = to_s ? s : tmp;
+    const int64_t out_stride = to_s ? n_sys : n_cols, out_col0 = to_s ? sys_begin : 0;
+    jacobi_sweep_global_kernel<<<grid, 256, 0, st>>>(in, in_stride, in_col0, u, n_sys, sys_begin, out, out_stride, out_col0, F,
+                                                     n_cols, radius, inv_diag, two_lambda, w);
+    in = out; in_stride = out_stride; in_col0 = out_col0;
+  }
+  return check_launch("jacobi_sweep_global");
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) {
@@ -322,9 +392,11 @@ static int launch_solve(const double* u, double* s, int F, int64_t n_sys, int64_
 }  // namespace mf
 
 extern "C" size_t mf_jacobi_workspace_bytes(int F, int64_t n_sys) {
-  (void)n_sys;
-  if (F <= 0) return 0;
-  return 2 * mf::align_up((size_t)F * sizeof(double), 256);
+  if (F <= 0 || n_sys <= 0) return 0;
+  size_t bytes = 2 * mf::align_up((size_t)F * sizeof(double), 256);
+  // beyond the on-chip kernels' frame limit the global-memory sweeps need a second trajectory buffer
+  if (F > mf::kOnChipMaxFrames) bytes += mf::global_scratch_bytes(F, n_sys);
+  return bytes;
 }
 
 extern "C" int mf_jacobi_solve(const double* u, const double* homographies, double* s, int F, int64_t n_sys,
@@ -339,6 +411,7 @@ extern "C" int mf_jacobi_solve(const double* u, const double* homographies, doub
   MF_REQUIRE((n_sys % 2) == 0 && (sys_begin % 2) == 0 && (sys_end % 2) == 0,
              "mf_jacobi_solve: systems come in (x, y) pairs; n_sys, sys_begin, sys_end must be even");
   MF_REQUIRE(0 <= sys_begin && sys_begin <= sys_end && sys_end <= n_sys, "mf_jacobi_solve: bad system range");
+  MF_REQUIRE((((uintptr_t)u | (uintptr_t)s) & 15u) == 0, "mf_jacobi_solve: u and s must be 16-byte aligned (the kernels read a vertex's (x, y) as one double2)");
   if (workspace_bytes < mf_jacobi_workspace_bytes(F, n_sys))
     return mf::fail(MF_E_WORKSPACE, "mf_jacobi_solve: workspace %zu < %zu bytes", workspace_bytes,
                     mf_jacobi_workspace_bytes(F, n_sys));
@@ -350,6 +423,12 @@ extern "C" int mf_jacobi_solve(const double* u, const double* homographies, doub
   if (int e = mf::check_launch("jacobi_coeff")) return e;
   const int64_t n_vert = (sys_end - sys_begin) / 2;
   if (n_vert == 0) return MF_OK;
+  if (mf::needs_global_path(F, radius)) {
+    if (F <= mf::kOnChipMaxFrames)
+      return mf::fail(MF_E_UNSUPPORTED, "mf_jacobi_solve: radius %d with %d frames does not fit shared memory", radius, F);
+    void* scratch = (char*)workspace + 2 * mf::align_up((size_t)F * sizeof(double), 256);
+    return mf::launch_global(u, s, F, n_sys, sys_begin, sys_end - sys_begin, radius, iterations, inv_diag, two_lambda, scratch, st);
+  }
   if (n_vert > 2147483647LL) return mf::fail(MF_E_UNSUPPORTED, "mf_jacobi_solve: too many vertices");
   if (radius == 10)
     return mf::launch_solve<10>(u, s, F, n_sys, sys_begin, n_vert, radius, iterations, inv_diag, two_lambda, st);

@@ -506,14 +506,19 @@ __global__ void __launch_bounds__(128) prefix_kernel(const float* __restrict__ v
   if (j >= n) return;
   double acc = disp0 ? disp0[j] : 0.0;
   disp[j] = acc;
+  // The scan itself must stay sequential (float64 additions in frame order, mfs.py:281), but the loads do not
+  // depend on it: eight frames are requested at once so that their L2 round trips overlap (the multi-GPU path
+  // scans world x F frames on every rank).
   int t = 0;
-  for (; t + 4 <= P; t += 4) {
-    const float a = vel[(size_t)t * n + j], b = vel[(size_t)(t + 1) * n + j];
-    const float c = vel[(size_t)(t + 2) * n + j], d = vel[(size_t)(t + 3) * n + j];
-    acc = MF_ADD(acc, (double)a); disp[(size_t)(t + 1) * n + j] = acc;
-    acc = MF_ADD(acc, (double)b); disp[(size_t)(t + 2) * n + j] = acc;
-    acc = MF_ADD(acc, (double)c); disp[(size_t)(t + 3) * n + j] = acc;
-    acc = MF_ADD(acc, (double)d); disp[(size_t)(t + 4) * n + j] = acc;
+  for (; t + 8 <= P; t += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = vel[(size_t)(t + k) * n + j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc = MF_ADD(acc, (double)v[k]);
+      disp[(size_t)(t + k + 1) * n + j] = acc;
+    }
   }
   for (; t < P; ++t) {
     acc = MF_ADD(acc, (double)vel[(size_t)t * n + j]);

@@ -205,12 +205,21 @@ __global__ void __launch_bounds__(128) tile_sort_kernel(const int* __restrict__ 
                                                         uint16_t* __restrict__ tile_list, int64_t ntiles_total, int ntiles,
                                                         int* __restrict__ edge_count, uint16_t* __restrict__ edge_tiles) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntiles_total) return;
-  const int craw = tile_count[t];
-  if ((craw & kEdgeFlag) && edge_count != nullptr) {        // tiles that hold a border cell: crop_edges_kernel's work list
-    const int f = (int)(t / ntiles);
-    edge_tiles[(size_t)f * ntiles + atomicAdd(&edge_count[f], 1)] = (uint16_t)(t - (int64_t)f * ntiles);
+  const bool in_range = t < ntiles_total;
+  const int craw = in_range ? tile_count[t] : 0;
+  // tiles that hold a border cell: crop_edges_kernel's work list.  One atomic per frame and warp: the lanes of a
+  // warp that tag tiles of the same frame share it.
+  const int f = in_range ? (int)(t / ntiles) : -1;
+  const bool tagged = in_range && (craw & kEdgeFlag) && edge_count != nullptr;
+  const unsigned peers = __match_any_sync(0xffffffffu, tagged ? f : -1 - (int)(threadIdx.x & 31));
+  if (tagged) {
+    const int lane = threadIdx.x & 31, leader = __ffs((int)peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&edge_count[f], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    edge_tiles[(size_t)f * ntiles + base + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)(t - (int64_t)f * ntiles);
   }
+  if (!in_range) return;
   const int n = craw & kCountMask;
   if (n < 2 || n > kTileCap) return;
   uint16_t* l = tile_list + t * kTileCap;

@@ -90,9 +90,13 @@ class MeshFlowStabilizer:
         if plan is not None and plan.world > 1:
             return self._stabilize_sharded(input_path, output_path, adaptive_weights_definition, plan)
         t0 = time.perf_counter()
-        frames, num_frames, fps, codec = self._get_unstabilized_frames_and_video_features(input_path)
+        # decode (mfs.py:172-213) with the front end of every decoded pair already running on the pool
+        pair_futures = []
+        with host_features.single_threaded_opencv():
+            frames, num_frames, fps, codec = self._get_unstabilized_frames_and_video_features(
+                input_path, on_frame=lambda fr: self._submit_pair(fr, pair_futures))
         t_decode = time.perf_counter() - t0
-        result = self.stabilize_frames(frames, adaptive_weights_definition, reuse_output=True)
+        result = self.stabilize_frames(frames, adaptive_weights_definition, reuse_output=True, pair_futures=pair_futures)
         t0 = time.perf_counter()
         self._write_stabilized_video(output_path, num_frames, fps, codec, result["cropped_frames"])
         self.last_timings = dict(result["timings"], decode=t_decode, encode=time.perf_counter() - t0)
@@ -101,7 +105,7 @@ class MeshFlowStabilizer:
         return (result["cropping_ratio"], result["distortion_score"], result["stability_score"])
 
     def stabilize_frames(self, unstabilized_frames, adaptive_weights_definition=ADAPTIVE_WEIGHTS_DEFINITION_ORIGINAL,
-                         with_metrics=True, plan=None, lookahead_frame=None, reuse_output=False):
+                         with_metrics=True, plan=None, lookahead_frame=None, reuse_output=False, pair_futures=None):
         """``stabilize()`` on in-memory frames: everything between decode and encode, device resident
         between the stages.  Returns a dict with the cropped frames, the crop rectangle, ``u``,
         ``homographies``, ``s`` (NumPy, whole video), the three metrics and per-stage wall times.
@@ -141,7 +145,10 @@ class MeshFlowStabilizer:
             a, b, self.mesh_outlier_subframe_row_count, self.mesh_outlier_subframe_col_count,
             self.homography_min_number_corresponding_features)
         with host_features.single_threaded_opencv():
-            futures = [pool.submit(track, frames[i], late[i]) for i in range(n_pairs)]
+            # ``pair_futures``: the caller already started the front end of the consecutive pairs (stabilize() does,
+            # while it decodes); only the look-ahead pair of a shard is still missing then
+            futures = list(pair_futures) if pair_futures is not None else []
+            futures += [pool.submit(track, frames[i], late[i]) for i in range(len(futures), n_pairs)]
             # -- 2. meanwhile: frames -> pinned memory -> device (resident when they fit, else streamed later)
             t0 = time.perf_counter()
             frame_bytes = height * width * 3
@@ -306,6 +313,16 @@ class MeshFlowStabilizer:
             self._streamed[id(core)] = sc
         return sc
 
+    def _track_job(self, early, late):
+        return host_features.track_pair(early, late, self.mesh_outlier_subframe_row_count,
+                                        self.mesh_outlier_subframe_col_count,
+                                        self.homography_min_number_corresponding_features)
+
+    def _submit_pair(self, frames_so_far, futures):
+        """Decode-time hook: the pair (previous frame, newest frame) goes to the pool at once."""
+        if len(frames_so_far) >= 2:
+            futures.append(self._thread_pool().submit(self._track_job, frames_so_far[-2], frames_so_far[-1]))
+
     def _thread_pool(self) -> ThreadPoolExecutor:
         if self._pool is None:
             workers = self.host_workers
@@ -404,8 +421,9 @@ class MeshFlowStabilizer:
     # ------------------------------------------------------------------------------------------
     # reference-named stage methods (NumPy in / NumPy out)
     # ------------------------------------------------------------------------------------------
-    def _get_unstabilized_frames_and_video_features(self, input_path):
-        """mfs.py:172-213 (host code, unchanged behaviour)."""
+    def _get_unstabilized_frames_and_video_features(self, input_path, on_frame=None):
+        """mfs.py:172-213 (host code, unchanged behaviour).  ``on_frame(frames_so_far)`` is called after every
+        decoded frame (stabilize() starts the feature tracking of the newest pair there)."""
         video = cv2.VideoCapture(input_path)
         num_frames = int(video.get(cv2.CAP_PROP_FRAME_COUNT))
         fps = video.get(cv2.CAP_PROP_FPS)
@@ -417,6 +435,8 @@ class MeshFlowStabilizer:
                 raise IOError(f'Video at <{input_path}> did not have frame {frame_index} of '
                               f'{num_frames} (indexed from 0).')
             frames.append(frame)
+            if on_frame is not None:
+                on_frame(frames)
         video.release()
         return (frames, num_frames, fps, codec)
 

@@ -165,3 +165,21 @@ def test_config3_geometry_streamed_equals_stage_sequence():
     assert torch.equal(core.warp_crop_bounds(u, s), crop_pf)
     ref = core.crop_resize_device(stab, enc).cpu().numpy()
     assert np.array_equal(h_out.numpy(), ref)
+
+
+def test_jacobi_beyond_the_on_chip_frame_limit():
+    """Videos longer than the on-chip kernels hold (F > 10 240) take the global-memory sweeps: same results
+    (sampled oracle), odd and even sweep counts (the ping-pong must end in the output), vertex shard respected."""
+    F, R, radius = 10400, 2, 10
+    rng = np.random.default_rng(31)
+    u, homs = synth.synthetic_paths(rng, F, R, R)
+    for iters in (7, 8):
+        core = _core(640, 360, R, R, radius=radius, iterations=iters)
+        ud, hd = _dev(u, core), _dev(homs, core)
+        s = core.stabilized_displacements(ud, hd, 0).cpu().numpy()
+        ref = spec.jacobi_banded(u, homs, 640, 360, radius, iters, 0)
+        assert np.abs(s - ref).max() <= 1e-9 * np.abs(ref).max()
+        out = torch.full((F, R + 1, R + 1, 2), -7.0, dtype=torch.float64, device=core.device)
+        core.stabilized_displacements(ud, hd, 0, vertex_range=(2, 5), out=out)
+        o = out.cpu().numpy().reshape(F, -1, 2)
+        assert np.array_equal(o[:, 2:5], s.reshape(F, -1, 2)[:, 2:5]) and np.all(o[:, :2] == -7.0) and np.all(o[:, 5:] == -7.0)
