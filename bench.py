@@ -72,6 +72,7 @@ def parse_args():
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api measurement")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity self-checks")
     ap.add_argument("--quick", action="store_true", help="kernel tuning: --no-cpu-baseline --no-api --no-parity")
+    ap.add_argument("--diag", action="store_true", help="N>1: per-rank solo step time and host enqueue time in the JSON line")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the streamed (e2e) schedule")
     ap.add_argument("--pixel-path", default="fused", choices=["fused", "two-kernel"],
@@ -166,12 +167,13 @@ def dist_setup():
     torch.cuda.set_device(local)
     # keep this rank's pinned host buffers (and the threads that fill them) on the GPU's own NUMA node:
     # with several ranks per box the host side of the copies is otherwise the bottleneck
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-    except Exception:
-        pass
+    if os.environ.get("MF_BENCH_NO_AFFINITY", "0") != "1":
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
@@ -358,6 +360,7 @@ def run_c2(args):
     lo = rank * F
 
     def hot_path(tr, frames_d, out_d, marks=None, keep=None):
+        nonlocal plan, lo
         def mark():
             if marks is not None:
                 e = ev(); e.record(); marks.append(e)
@@ -385,20 +388,24 @@ def run_c2(args):
     for _ in range(args.warmup):
         hot_path(d_tracks, d_frames, d_out)
     barrier(world)
-    sampler = ClockSampler(local)
-    sampler.start()
+    # rank 0 reports the clocks; the other ranks do not poll NVML next to their launch thread
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     t_begin, t_end = ev(), ev()
     marks_all = []
     barrier(world)
     t_begin.record()
     kept = {}
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         marks = []
         enc, score = hot_path(d_tracks, d_frames, d_out, marks, kept)
         marks_all.append(marks)
     t_end.record()
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps
     barrier(world)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     ms_total = t_begin.elapsed_time(t_end)
     stage_ms = {n: 0.0 for n in stage_names}
     for marks in marks_all:
@@ -454,6 +461,27 @@ def run_c2(args):
     barrier(world)
     ms_e2e = e0.elapsed_time(e1)
 
+    diag = None
+    if args.diag and world > 1:
+        # every rank alone (no plan, no collectives) on its own frames, and how long the host needs to enqueue a step
+        saved_plan, plan = plan, None
+        lo_saved, lo = lo, 0
+        for _ in range(2):
+            hot_path(d_tracks, d_frames, d_out)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        th = time.perf_counter()
+        for _ in range(args.steps):
+            hot_path(d_tracks, d_frames, d_out)
+        solo_host = (time.perf_counter() - th) * 1e3 / args.steps
+        e1.record()
+        torch.cuda.synchronize()
+        plan, lo = saved_plan, lo_saved
+        mine = torch.tensor([e0.elapsed_time(e1) / args.steps, solo_host, host_enqueue_ms], dtype=torch.float64, device=dev)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        diag = {"per_rank [solo step ms, solo host enqueue ms, sharded host enqueue ms]": [[round(x, 3) for x in v.tolist()] for v in allv]}
     ms_total, ms_e2e = max_over_ranks([ms_total, ms_e2e], world, dev)
     if rank != 0:
         if world > 1:
@@ -504,6 +532,8 @@ def run_c2(args):
                    "note": "HBM is touched twice (load b, store x): the solve is bound by shared memory and the float64 pipe"},
         "clocks": clocks,
     }
+    if diag:
+        out["diag"] = diag
     if world == 1:
         if not args.no_parity:
             out["parity_checked"], out["parity"] = parity_self_check(args, core, frames, packed, d_frames, d_out, kept)
@@ -647,14 +677,16 @@ def run_c3(args):
     for _ in range(args.warmup):
         enc, _ = step()
     barrier(world)
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None    # one NVML poller per box, not one per rank
+    if sampler:
+        sampler.start()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
         enc, score = step()
     e1.record()
     barrier(world)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     (ms,) = max_over_ranks([e0.elapsed_time(e1)], world, dev)
     if rank == 0:
         fps = Ftot * args.steps / (ms / 1e3)

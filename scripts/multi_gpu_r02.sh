@@ -2,7 +2,7 @@
 # Multi-GPU evidence of round 2, run under `gpurun --gpus N`:  scripts/multi_gpu_r02.sh N [c2 c3 c4 c5 test]
 # Keeps one JSON line per configuration under gpurun_out/ (copied to profiles/ for the record).
 n=${1:-2}; shift
-what=${@:-"test c2 c3 c4 c5"}
+what=${@:-"test c2 c3 c4 c5 pcie"}
 mkdir -p gpurun_out
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "$@"; }
 for w in $what; do
@@ -12,6 +12,7 @@ for w in $what; do
     c3) run bench.py --gpus $n --config c3 --steps 2 --warmup 1 > gpurun_out/r02_c3_N${n}.json 2> gpurun_out/r02_c3_N${n}.err;;
     c4) run bench.py --gpus $n --config c4 --steps 3 --warmup 1 > gpurun_out/r02_c4_N${n}.json 2> gpurun_out/r02_c4_N${n}.err;;
     c5) run bench.py --gpus $n --config c5 --steps 3 --warmup 2 > gpurun_out/r02_c5_N${n}.json 2> gpurun_out/r02_c5_N${n}.err;;
+    pcie) run scripts/pcie_probe.py --bind > gpurun_out/r02_pcie_N${n}.json 2> gpurun_out/r02_pcie_N${n}.err; tail -1 gpurun_out/r02_pcie_N${n}.json;;
   esac
   for f in gpurun_out/r02_${w}_N${n}.json; do [ -f "$f" ] && python - "$f" <<'PY'
 import json, sys
