@@ -7,11 +7,13 @@ fixed-point models of the OpenCV primitives the reference leans on (``cv2.remap`
 what the CUDA kernels are compared with at sizes the port cannot reach (1080p+, F = 10 000).
 
 Pinning: every function here is asserted equal to ``reference_port`` (itself pinned bit-for-bit to
-the unmodified reference) by ``tests/test_oracle_spec.py`` and by ``tests/golden/make_golden.py``.
+the unmodified reference) by ``tests/test_oracle.py`` (seeded inputs up to 1920x1080 and the committed goldens) and by
+``tests/golden/make_golden.py`` (against the reference itself).
 The OpenCV models were checked against opencv-python-headless 4.13.0; a different wheel that changes
 them makes those tests fail loudly.
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs (cpu_baseline, --impl reference, the
+parity self-check outside the timed region) may import this.
 References are to meshflowstabilizer.py (``mfs.py:N``).
 """
 from __future__ import annotations
