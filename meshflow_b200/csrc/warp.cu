@@ -781,7 +781,7 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
                                                                        w.edge_count, w.edge_tiles);
   if (int e = mf::check_launch("tile_sort")) return e;
   if (fast) {
-    const int64_t nspan = ncells * ((w.span_rows + mf::kSpanRowsPerThread - 1) / mf::kSpanRowsPerThread);
+    const int64_t nspan = ncells * mf::kSpanChunks;
     mf::cell_spans_kernel<<<(unsigned)((nspan + 127) / 128), 128, 0, st>>>(w.cells, w.spans, ncells, w.span_rows, w.span_tab);
     if (int e = mf::check_launch("cell_spans")) return e;
     const int64_t nrows = (int64_t)nf * H * tiles_x;

@@ -49,31 +49,37 @@ static constexpr uint32_t kSpanEmpty = 0x00000001u;          // a = 1, b = 0
 
 static constexpr int kSpanRowsPerThread = 4;                 // independent rows per thread: four chains in flight
 
+// Thread = (frame, cell, chunk of four rows).  A cell's box is rarely taller than 1.5 x the cell, far less than the
+// span table's row capacity, so only kSpanChunks chunks are launched per cell and a thread strides over the box
+// (round 1 launched one thread per table chunk: 40 % of the lanes had nothing to do).
+static constexpr int kSpanChunks = 24;
+
 __global__ void __launch_bounds__(128) cell_spans_kernel(const Cell* __restrict__ cells, const CellSpan* __restrict__ spans,
                                                          int64_t ncells_total, int span_rows, uint32_t* __restrict__ span_tab) {
-  const int chunks = (span_rows + kSpanRowsPerThread - 1) / kSpanRowsPerThread;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= ncells_total * chunks) return;
-  const int64_t cid = idx / chunks;
-  const int rl0 = (int)(idx - cid * chunks) * kSpanRowsPerThread;
+  if (idx >= ncells_total * kSpanChunks) return;
+  const int64_t cid = idx / kSpanChunks;
+  const int chunk = (int)(idx - cid * kSpanChunks);
   const Cell& c = cells[cid];
   const int4 box = __ldg(reinterpret_cast<const int4*>(&c));
-  if (box.x > box.z || box.y + rl0 > box.w) return;
+  if (box.x > box.z || box.y + chunk * kSpanRowsPerThread > box.w) return;
   const CellSpan& sp = spans[cid];
   const bool regular = sp.regular != 0;
   uint32_t* out = span_tab + cid * span_rows;
+  for (int rl0 = chunk * kSpanRowsPerThread; rl0 < span_rows && box.y + rl0 <= box.w; rl0 += kSpanChunks * kSpanRowsPerThread) {
 #pragma unroll
-  for (int k = 0; k < kSpanRowsPerThread; ++k) {
-    const int rl = rl0 + k, y = box.y + rl;
-    if (rl >= span_rows || y > box.w) break;
-    uint32_t v = kSpanIrregular;
-    if (regular) {
-      int a, b;
-      const int st = span_of_row(c, sp, y, box.x, box.z, a, b);
-      if (st == 0) v = (uint32_t)a | ((uint32_t)b << 16);
-      else if (st == 1) v = kSpanEmpty;
+    for (int k = 0; k < kSpanRowsPerThread; ++k) {
+      const int rl = rl0 + k, y = box.y + rl;
+      if (rl >= span_rows || y > box.w) break;
+      uint32_t v = kSpanIrregular;
+      if (regular) {
+        int a, b;
+        const int st = span_of_row(c, sp, y, box.x, box.z, a, b);
+        if (st == 0) v = (uint32_t)a | ((uint32_t)b << 16);
+        else if (st == 1) v = kSpanEmpty;
+      }
+      out[rl] = v;
     }
-    out[rl] = v;
   }
 }
 

@@ -34,6 +34,17 @@ try:
         except OSError as e:
             out.setdefault("load_errors", []).append(f"{name}: {e}")
     if lib is not None:
+        # make sure a driver-API context is current on this thread (torch's primary context normally is)
+        cu = ctypes.CDLL("libcuda.so.1")
+        ctx = ctypes.c_void_p()
+        out["cuInit_rc"] = int(cu.cuInit(0))
+        out["cuCtxGetCurrent_rc"] = int(cu.cuCtxGetCurrent(ctypes.byref(ctx)))
+        out["ctx_current"] = bool(ctx.value)
+        if not ctx.value:
+            dev = ctypes.c_int()
+            cu.cuDeviceGet(ctypes.byref(dev), 0)
+            out["cuDevicePrimaryCtxRetain_rc"] = int(cu.cuDevicePrimaryCtxRetain(ctypes.byref(ctx), dev))
+            out["cuCtxSetCurrent_rc"] = int(cu.cuCtxSetCurrent(ctx))
         caps = CUVIDDECODECAPS()
         caps.eCodecType, caps.eChromaFormat, caps.nBitDepthMinus8 = 4, 1, 0      # H.264, 4:2:0, 8 bit
         rc = lib.cuvidGetDecoderCaps(ctypes.byref(caps))
