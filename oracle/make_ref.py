@@ -4,7 +4,7 @@ The reference (how4rd/meshflow) is one pure-Python file with no build system (no
 ``pip install /root/reference`` has nothing to install), so "building" it means copying, byte for byte,
 
     /root/reference/meshflowstabilizer.py               -> baseline/_ref/meshflowstabilizer.py
-    /root/reference/videos/video-1/video-1.m4v          -> baseline/_ref/video-1.m4v
+    /root/reference/videos/video-N/video-N.m4v          -> baseline/_ref/video-N.m4v    (the seven input clips, 14 MB)
 
 ``baseline/_ref/`` is git-ignored (the reference's sources never enter this repository's history) but NOT
 gpurun-ignored, so the copy travels to the GPU box, where ``/root/reference`` does not exist.  It is used
@@ -21,7 +21,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference"
 DST = os.path.join(ROOT, "baseline", "_ref")
-FILES = {"meshflowstabilizer.py": "meshflowstabilizer.py", "videos/video-1/video-1.m4v": "video-1.m4v"}
+VIDEOS = (1, 2, 3, 5, 8, 9, 10)
+FILES = {"meshflowstabilizer.py": "meshflowstabilizer.py"}
+FILES.update({f"videos/video-{n}/video-{n}.m4v": f"video-{n}.m4v" for n in VIDEOS})
 
 
 def stage(verbose=True):
@@ -60,8 +62,8 @@ def reference_module():
     return mod
 
 
-def video_path():
-    path = os.path.join(DST, "video-1.m4v")
+def video_path(n=1):
+    path = os.path.join(DST, f"video-{n}.m4v")
     return path if os.path.exists(path) else None
 
 

@@ -40,6 +40,7 @@ tqdm.trange = lambda n: contextlib.nullcontext(
 import meshflowstabilizer as ref  # noqa: E402
 
 VIDEO = "/root/reference/videos/video-1/video-1.m4v"
+# python tests/golden/make_golden_c1.py --video N [--definitions 0,2]  ->  tests/golden/videoN_full.npz
 
 
 def sha(a):
@@ -47,9 +48,17 @@ def sha(a):
 
 
 def main():
-    limit = int(sys.argv[1]) if len(sys.argv) > 1 else None      # frame limit for a quick dry run
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("limit", nargs="?", type=int, default=None, help="frame limit for a quick dry run")
+    ap.add_argument("--video", type=int, default=1)
+    ap.add_argument("--definitions", default="0,1,2,3")
+    a = ap.parse_args()
+    limit = a.limit
+    video = f"/root/reference/videos/video-{a.video}/video-{a.video}.m4v"
+    definitions = [int(d) for d in a.definitions.split(",")]
     R = ref.MeshFlowStabilizer()
-    frames, num_frames, fps, codec = R._get_unstabilized_frames_and_video_features(VIDEO)
+    frames, num_frames, fps, codec = R._get_unstabilized_frames_and_video_features(video)
     if limit:
         frames, num_frames = frames[:limit], limit
     h, w = frames[0].shape[:2]
@@ -62,7 +71,7 @@ def main():
                num_frames=np.array(num_frames), frame_size=np.array([w, h]), sample_vertices=sample,
                u_sha=np.array(sha(u)), homographies_sha=np.array(sha(homs)), homographies=homs,
                u_sample=u.reshape(num_frames, V, 2)[:, sample], frames_sha=np.array(sha(np.stack(frames))))
-    for d in range(4):
+    for d in definitions:
         t0 = time.time()
         lam = R._get_adaptive_weights(num_frames, w, h, d, homs)
         s = R._get_stabilized_vertex_displacements(num_frames, frames, d, u, homs)
@@ -80,7 +89,7 @@ def main():
         out[f"cropped_sha_{d}"] = np.array(sha(np.stack(cropped)))
         print(f"definition {d}: {time.time() - t0:.1f} s  crop {tuple(int(c) for c in crop)} tuple "
               f"({float(cr)!r}, {float(ds)!r}, {float(st)!r}) cropped sha {out[f'cropped_sha_{d}']}", flush=True)
-        name = "video1_full.npz" if not limit else f"video1_first{limit}.npz"
+        name = f"video{a.video}_full.npz" if not limit else f"video{a.video}_first{limit}.npz"
         np.savez_compressed(os.path.join(HERE, name), **out)       # after every definition: a partial record survives
 
 

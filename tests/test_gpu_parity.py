@@ -327,6 +327,15 @@ def test_streamed_schedule_equals_stage_sequence():
         assert core.decode_crop(enc2) == core.decode_crop(enc)
         assert torch.equal(u2, u) and torch.equal(s2, s)
         assert np.array_equal(h_out.numpy(), ref)
+    # long videos: no table budget -> crop rectangle chunk by chunk, tables rebuilt per chunk in pass B;
+    # frames already resident on the device; every landed chunk reported to the host in order
+    h_out.zero_()
+    landed = []
+    sc0 = StreamedCore(core, chunk_frames=4, table_budget_bytes=0)
+    enc3, u3, s3 = sc0.run(None, tracks, h_out, 2, d_frames=_dev(frames, core), on_chunk_landed=lambda f0, n: landed.append((f0, n)))
+    assert core.decode_crop(enc3) == core.decode_crop(enc) and torch.equal(s3, s)
+    assert np.array_equal(h_out.numpy(), ref)
+    assert [f0 for f0, _ in landed] == sorted(f0 for f0, _ in landed) and sum(n for _, n in landed) == F
 
 
 def test_stabilize_frames_matches_the_reference_port_end_to_end():
