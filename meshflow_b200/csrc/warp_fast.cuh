@@ -19,7 +19,7 @@
 //                         mfs.py:909-1100).  CTA = 128 x 120 output pixels, warp = 128 x 15.
 //   warp_fused_kernel   : pass B of the streamed schedule.  The crop rectangle is already known, so a CTA
 //                         produces the stabilized pixels of ONE 120 x 64 tile of the FINAL frame (+ the one
-//                         row / column of overlap cv2.resize's taps need) into shared memory and resizes
+//                         row / column of overlap cv2.resize's taps need) into shared memory (BGRx) and resizes
 //                         from there (mfs.py:1111-1157): the stabilized frame never exists in DRAM and the
 //                         pixels outside the crop rectangle are never computed.
 //
@@ -251,8 +251,9 @@ struct PixelSink {
   uint8_t* base;
   unsigned pitch;
   int ox, oy;
+  unsigned px_bytes;          // 3: packed BGR (frames in global memory); 4: BGRx (the fused kernel's shared-memory tile)
   __device__ __forceinline__ uint8_t* at(int px, int py) const {
-    return base + (size_t)(py - oy) * pitch + (size_t)(px - ox) * 3;
+    return base + (size_t)(py - oy) * pitch + (size_t)(px - ox) * px_bytes;
   }
 };
 
@@ -412,7 +413,9 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
   const size_t own_stride = (size_t)T.tiles_x * 32;
   const uint16_t* own = T.lane_owner + ((size_t)f * H + y_first) * own_stride + min(px0 >> 2, T.tiles_x * 32 - 1);
   uint8_t* drow = kShared ? nullptr : sink.at(px0, y_first);
-  unsigned srow = kShared ? sink_shared + (unsigned)(y_first - sink.oy) * sink.pitch + (unsigned)(px0 - sink.ox) * 3u : 0u;
+  // the shared-memory tile holds BGRx pixels: a group is one aligned 16-byte store, and the resize phase reads taps as
+  // whole words (no byte phases)
+  unsigned srow = kShared ? sink_shared + (unsigned)(y_first - sink.oy) * sink.pitch + (unsigned)(px0 - sink.ox) * 4u : 0u;
   const CellFast* ffast = T.fast + fcell0;
   const unsigned lt_mask = (1u << lane) - 1u;
   // the lists' shared-window addresses, once: generic pointers would be re-derived (S2R + LEA) every row
@@ -439,11 +442,8 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
         } else if (id != kSegNone || npx < kPix) {
           flag = all;
         } else {                                             // no cell: map (W+1, H+1), border colour
-          const uint32_t w0 = border | (border << 24), w1 = (border >> 8) | (border << 16), w2 = (border >> 16) | (border << 8);
           if (kShared) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(srow), "r"(w0));
-            asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(srow), "r"(w1));
-            asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(srow), "r"(w2));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(srow), "r"(border));
           } else {
             uint32_t o[kPix] = {border, border, border, border};
             store_bgr4(drow, o, kPix, word_store);
@@ -504,14 +504,15 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
       blend_group_pixel<1>(st, sb, nu[1] - bu - 32u, nv[1] - bv, vb[1], vg[1], vr[1]);
       blend_group_pixel<2>(st, sb, nu[2] - bu - 64u, nv[2] - bv, vb[2], vg[2], vr[2]);
       blend_group_pixel<3>(st, sb, nu[3] - bu - 96u, nv[3] - bv, vb[3], vg[3], vr[3]);
-      const uint32_t o0 = __byte_perm(__byte_perm(vb[0], vg[0], 0x0040), __byte_perm(vr[0], vb[1], 0x0040), 0x5410);
-      const uint32_t o1 = __byte_perm(__byte_perm(vg[1], vr[1], 0x0040), __byte_perm(vb[2], vg[2], 0x0040), 0x5410);
-      const uint32_t o2 = __byte_perm(__byte_perm(vr[2], vb[3], 0x0040), __byte_perm(vg[3], vr[3], 0x0040), 0x5410);
       if (kShared) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(srow), "r"(o0));
-        asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(srow), "r"(o1));
-        asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(srow), "r"(o2));
+        uint32_t p[kPix];
+#pragma unroll
+        for (int j = 0; j < kPix; ++j) p[j] = __byte_perm(__byte_perm(vb[j], vg[j], 0x0040), vr[j], 0x0410);   // B G R x
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(srow), "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]));
       } else if (word_store) {
+        const uint32_t o0 = __byte_perm(__byte_perm(vb[0], vg[0], 0x0040), __byte_perm(vr[0], vb[1], 0x0040), 0x5410);
+        const uint32_t o1 = __byte_perm(__byte_perm(vg[1], vr[1], 0x0040), __byte_perm(vb[2], vg[2], 0x0040), 0x5410);
+        const uint32_t o2 = __byte_perm(__byte_perm(vr[2], vb[3], 0x0040), __byte_perm(vg[3], vr[3], 0x0040), 0x5410);
         uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
         __stcs(d32 + 0, o0); __stcs(d32 + 1, o1); __stcs(d32 + 2, o2);
       } else {
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FAST_MINBLOCKS) warp_fast_ker
   if (nrows <= 0) return;
   PixelSink sink;
   sink.base = frames_out + (size_t)f * H * W * 3;
-  sink.pitch = (unsigned)W * 3u; sink.ox = 0; sink.oy = 0;
+  sink.pitch = (unsigned)W * 3u; sink.ox = 0; sink.oy = 0; sink.px_bytes = 3u;
   warp_rows<false>(frames_in + (size_t)f * H * W * 3, T, f, W, H, blockIdx.x * kTileW, y_first, nrows, 0, W - 1, sink, 0u,
                    border, scratch[warp].med, scratch[warp].ex, scratch[warp].slow, lane);
 }
@@ -634,7 +635,7 @@ static constexpr int kOutTileH = MF_FUSED_TILE_H;           // eight rows per wa
 static_assert(kOutTileH % 8 == 0 && kOutTileH >= 8 && kOutTileH <= 120, "resize phase: whole rows per warp");
 static constexpr int kStabRows = kOutTileH + 1;             // scale <= 1: at most one source row more than output rows
 static constexpr int kStabRowsPerWarp = (kStabRows + 7) / 8;
-static constexpr int kStabPitch = kTileW * 3;               // 384 B: 128 stabilized pixels per row
+static constexpr int kStabPitch = kTileW * 4;               // 512 B: 128 stabilized BGRx pixels per row
 static_assert(kStabRowsPerWarp <= 16 && kStabRowsPerWarp * 8 >= kStabRows, "rows of the stabilized tile split over eight warps");
 
 struct FusedShared {
@@ -642,19 +643,17 @@ struct FusedShared {
   WarpScratch<kStabRowsPerWarp> scratch[kWarpThreads / 32];
 };
 
-// Horizontal pass of cv2.resize for the four pixels of a thread on one row of the shared-memory tile:
-// (a0 * p[c0] + a1 * p[c0 + 1]) >> 4 per channel.  boff[j] = byte offset of pixel j's left tap in the row.
-__device__ __forceinline__ void fused_hsum(unsigned row_shared, const unsigned (&woff)[kPix], const unsigned (&shift)[kPix],
-                                           const uint32_t (&wx)[kPix], RowSums& out) {
+// Horizontal pass of cv2.resize for the four pixels of a thread on one row of the shared-memory tile (BGRx words):
+// (a0 * p[c0] + a1 * p[c0 + 1]) >> 4 per channel.  woff[j] = byte offset of pixel j's left tap in the row.
+__device__ __forceinline__ void fused_hsum(unsigned row_shared, const unsigned (&woff)[kPix], const uint32_t (&wx)[kPix],
+                                           RowSums& out) {
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    uint32_t t0, t1, t2;
+    uint32_t t0, t1;
     const unsigned a = row_shared + woff[j];
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t0) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(t1) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(t2) : "r"(a));
-    const uint32_t u0 = __funnelshift_r(t0, t1, shift[j]), u1 = __funnelshift_r(t1, t2, shift[j]);   // B0 G0 R0 B1 | G1 R1 . .
-    const uint32_t bg = __byte_perm(u0, u1, 0x4130), rr = __byte_perm(u0, u1, 0x0052);
+    const uint32_t bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x0062);   // B0 B1 G0 G1 | R0 R1 . .
     out.v[j][0] = __dp2a_lo(wx[j], bg, 0u) >> 4;
     out.v[j][1] = __dp2a_hi(wx[j], bg, 0u) >> 4;
     out.v[j][2] = __dp2a_lo(wx[j], rr, 0u) >> 4;
@@ -689,7 +688,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_k
   const int total = yb - ya + 1, base = total >> 3, extra = total & 7;
   {
     PixelSink sink;
-    sink.base = sm.tile; sink.pitch = kStabPitch; sink.ox = X0; sink.oy = ya;
+    sink.base = sm.tile; sink.pitch = kStabPitch; sink.ox = X0; sink.oy = ya; sink.px_bytes = 4u;
     const int y_first = ya + warp * base + min(warp, extra);
     const int nrows = base + (warp < extra ? 1 : 0);
 #ifdef MF_EXP_NO_WARP                  // timing experiment only: cost of the resize phase alone
@@ -714,14 +713,13 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_k
   const unsigned out_pitch = (unsigned)W * 3u;
   uint8_t* drow = frames_out + ((size_t)fl * H * W + (size_t)y_out0 * W + px0) * 3;
   uint32_t wx[kPix];
-  unsigned woff[kPix], shift[kPix];
+  unsigned woff[kPix];
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
     const int4 xt = __ldg(xtab + min(px0 + j, W - 1));
     // the right tap of a pixel clamped at the crop's last column carries weight 0: reading c0 + 1 is harmless
     wx[j] = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
-    const unsigned b = (unsigned)(left + xt.x - X0) * 3u;
-    woff[j] = b & ~3u; shift[j] = (b & 3u) * 8u;
+    woff[j] = (unsigned)(left + xt.x - X0) * 4u;
   }
   const bool word_store = npx == kPix && (out_pitch & 3u) == 0u && (reinterpret_cast<uintptr_t>(drow) & 3u) == 0u;
   RowSums P, Q;
@@ -749,17 +747,17 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_k
   // Tt holds source row rt in the top role, M holds rm in the bottom role; returns true when the roles swapped
   auto step = [&](RowSums& Tt, RowSums& M, int& rt, int& rm, int r0, int r1, const int4& yt) -> bool {
     if (r0 != rt && r0 == rm && r1 != rm) {                  // the usual move: old bottom becomes top, one new row
-      fused_hsum(tile_shared + (unsigned)(r1 - ya) * kStabPitch, woff, shift, wx, Tt);
+      fused_hsum(tile_shared + (unsigned)(r1 - ya) * kStabPitch, woff, wx, Tt);
       rt = r1;
       vertical(M, Tt, yt);
       return true;
     }
     if (r0 != rt) {
-      if (r0 == rm) Tt = M; else fused_hsum(tile_shared + (unsigned)(r0 - ya) * kStabPitch, woff, shift, wx, Tt);
+      if (r0 == rm) Tt = M; else fused_hsum(tile_shared + (unsigned)(r0 - ya) * kStabPitch, woff, wx, Tt);
       rt = r0;
     }
     if (r1 != rm) {
-      if (r1 == rt) M = Tt; else fused_hsum(tile_shared + (unsigned)(r1 - ya) * kStabPitch, woff, shift, wx, M);
+      if (r1 == rt) M = Tt; else fused_hsum(tile_shared + (unsigned)(r1 - ya) * kStabPitch, woff, wx, M);
       rm = r1;
     }
     vertical(Tt, M, yt);
@@ -770,7 +768,7 @@ __global__ void __launch_bounds__(kWarpThreads, MF_FUSED_MINBLOCKS) warp_fused_k
     // prologue: the first output row's top source row enters in the bottom role, so that the first step is already
     // "the usual move" (one new row) and the general form stays out of the common path
     rq = top + __ldg(ytab + y_out0).x;
-    fused_hsum(tile_shared + (unsigned)(rq - ya) * kStabPitch, woff, shift, wx, Q);
+    fused_hsum(tile_shared + (unsigned)(rq - ya) * kStabPitch, woff, wx, Q);
   }
 #endif
   int4 yt_next = __ldg(ytab + y_out0);
