@@ -485,6 +485,19 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
       const uint32_t* w0 = reinterpret_cast<const uint32_t*>(p0 & ~(uintptr_t)3);
       const uint32_t* w1 = reinterpret_cast<const uint32_t*>(p1 & ~(uintptr_t)3);
       uint32_t t[5], b[5];
+#ifdef MF_EXP_TAP_MASK
+      // EXPERIMENT (results invalid): the taps of the fast path read from shared memory with 32-bit addresses, as if
+      // the tile's source box had been staged there for free (TMA): an upper bound on what staging can bring.
+      {
+        const unsigned o0 = ((unsigned)iy0 * pitch + (unsigned)ix0 * 3u);
+        const unsigned s0 = o0 & (unsigned)MF_EXP_TAP_MASK & ~3u, s1 = (o0 + pitch) & (unsigned)MF_EXP_TAP_MASK & ~3u;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t[i]) : "r"(s0 + 4u * i));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b[i]) : "r"(s1 + 4u * i));
+        }
+      }
+#else
 #pragma unroll
       for (int i = 0; i < 4; ++i) { t[i] = __ldg(w0 + i); b[i] = __ldg(w1 + i); }
 #ifndef MF_FAST_NO_PREFETCH
@@ -493,6 +506,7 @@ __device__ __forceinline__ void warp_rows(const uint8_t* __restrict__ src, const
 #endif
       t[4] = f0 >= 2u ? __ldg(w0 + 4) : 0u;
       b[4] = f1 >= 2u ? __ldg(w1 + 4) : 0u;
+#endif
       uint32_t st[4], sb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -641,6 +655,9 @@ static_assert(kStabRowsPerWarp <= 16 && kStabRowsPerWarp * 8 >= kStabRows, "rows
 struct FusedShared {
   uint8_t tile[kStabRows * kStabPitch + 32];               // + slack: a zero-weight tap may read past the last pixel
   WarpScratch<kStabRowsPerWarp> scratch[kWarpThreads / 32];
+#ifdef MF_EXP_EXTRA_SMEM
+  uint8_t exp_box[MF_EXP_EXTRA_SMEM];                        // EXPERIMENT: the shared memory a staged source box would take
+#endif
 };
 
 // Horizontal pass of cv2.resize for the four pixels of a thread on one row of the shared-memory tile (BGRx words):
