@@ -23,6 +23,7 @@
 #define MF_ADD(a, b) __dadd_rn((a), (b))
 #define MF_SUB(a, b) __dsub_rn((a), (b))
 #define MF_DIV(a, b) __ddiv_rn((a), (b))
+#define MF_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define MF_SQRT(a) __dsqrt_rn((a))
 #define MF_FMUL(a, b) __fmul_rn((a), (b))
 #define MF_FADD(a, b) __fadd_rn((a), (b))
@@ -32,6 +33,7 @@
 #define MF_ADD(a, b) ((a) + (b))
 #define MF_SUB(a, b) ((a) - (b))
 #define MF_DIV(a, b) ((a) / (b))
+#define MF_FMA(a, b, c) fma((a), (b), (c))
 #define MF_SQRT(a) sqrt((a))
 #define MF_FMUL(a, b) ((a) * (b))
 #define MF_FADD(a, b) ((a) + (b))
@@ -73,12 +75,21 @@ MF_HD int round_sat_f(float v) {
 // ---------------------------------------------------------------------------------------------
 // cv2.perspectiveTransform, float64 arithmetic:  w = 1/w (0 when |w| <= DBL_EPSILON), then multiply.
 // (mfs.py:325, 420, 1054)
+//
+// The sums x*m0 + y*m1 + m2 are evaluated the way OpenCV's binary evaluates them on every x86-64 CPU with FMA3
+// (perspectiveTransform_ in core/src/matmul.simd.hpp is built per CPU dispatch level -- AVX2, AVX-512 -- with GCC's
+// default -ffp-contract=fast):  fma(x, m0, y*m1) + m2  -- y*m1 rounded, x*m0 fused, m2 added last.  Pinned against
+// cv2 itself (tests/test_oracle.py) and by the reference's output on videos/video-2, whose first frame pair is almost
+// static: its residuals late - H(early) are ~1e-6 px, so a last-bit difference in H(early) shows in the float32
+// velocity.  (A CPU without FMA would run the baseline build and round x*m0 separately.)
 // ---------------------------------------------------------------------------------------------
+MF_HD double persp_sum(double x, double a, double yb, double c) { return MF_ADD(MF_FMA(x, a, yb), c); }
+
 MF_HD void persp(const double* M, double x, double y, double& ox, double& oy) {
-  double w = MF_ADD(MF_ADD(MF_MUL(x, M[6]), MF_MUL(y, M[7])), M[8]);
+  double w = persp_sum(x, M[6], MF_MUL(y, M[7]), M[8]);
   w = (fabs(w) > 2.220446049250313e-16) ? MF_DIV(1.0, w) : 0.0;
-  ox = MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, M[0]), MF_MUL(y, M[1])), M[2]), w);
-  oy = MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, M[3]), MF_MUL(y, M[4])), M[5]), w);
+  ox = MF_MUL(persp_sum(x, M[0], MF_MUL(y, M[1]), M[2]), w);
+  oy = MF_MUL(persp_sum(x, M[3], MF_MUL(y, M[4]), M[5]), w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,10 +440,10 @@ MF_HD unsigned cell_screen_sides(const Cell& c, float x, float bx, float by, flo
 
 // float32 remap coordinates of output pixel (x, y) through the cell (mfs.py:1054)
 MF_HD void cell_map(const Cell& c, double x, double y, float& mx, float& my) {
-  double w = MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[6]), MF_MUL(y, c.Hsu[7])), 1.0);
+  double w = persp_sum(x, c.Hsu[6], MF_MUL(y, c.Hsu[7]), 1.0);
   w = (fabs(w) > 2.220446049250313e-16) ? MF_DIV(1.0, w) : 0.0;
-  mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[0]), MF_MUL(y, c.Hsu[1])), c.Hsu[2]), w);
-  my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[3]), MF_MUL(y, c.Hsu[4])), c.Hsu[5]), w);
+  mx = (float)MF_MUL(persp_sum(x, c.Hsu[0], MF_MUL(y, c.Hsu[1]), c.Hsu[2]), w);
+  my = (float)MF_MUL(persp_sum(x, c.Hsu[3], MF_MUL(y, c.Hsu[4]), c.Hsu[5]), w);
 }
 
 // cell_map with the row products y*Hsu[1], y*Hsu[4], y*Hsu[7] supplied by the caller: every rounding
@@ -456,26 +467,26 @@ __device__ __forceinline__ double rcp_rn_normal(double w) {
 
 MF_HD void map_row(double h0, double h2, double h3, double h5, double h6, double x, double yh1, double yh4,
                    double yh7, float& mx, float& my) {
-  double w = MF_ADD(MF_ADD(MF_MUL(x, h6), yh7), 1.0);
+  double w = persp_sum(x, h6, yh7, 1.0);
 #if defined(__CUDA_ARCH__)
   const double aw = fabs(w);
   w = (aw > 1e-100 && aw < 1e100) ? rcp_rn_normal(w) : ((aw > 2.220446049250313e-16) ? __drcp_rn(w) : 0.0);
 #else
   w = (fabs(w) > 2.220446049250313e-16) ? (1.0 / w) : 0.0;
 #endif
-  mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, h0), yh1), h2), w);
-  my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, h3), yh4), h5), w);
+  mx = (float)MF_MUL(persp_sum(x, h0, yh1, h2), w);
+  my = (float)MF_MUL(persp_sum(x, h3, yh4, h5), w);
 }
 
 MF_HD void cell_map_row(const Cell& c, double x, double yh1, double yh4, double yh7, float& mx, float& my) {
-  double w = MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[6]), yh7), 1.0);
+  double w = persp_sum(x, c.Hsu[6], yh7, 1.0);
 #if defined(__CUDA_ARCH__)
   w = (fabs(w) > 2.220446049250313e-16) ? __drcp_rn(w) : 0.0;
 #else
   w = (fabs(w) > 2.220446049250313e-16) ? (1.0 / w) : 0.0;
 #endif
-  mx = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[0]), yh1), c.Hsu[2]), w);
-  my = (float)MF_MUL(MF_ADD(MF_ADD(MF_MUL(x, c.Hsu[3]), yh4), c.Hsu[5]), w);
+  mx = (float)MF_MUL(persp_sum(x, c.Hsu[0], yh1, c.Hsu[2]), w);
+  my = (float)MF_MUL(persp_sum(x, c.Hsu[3], yh4, c.Hsu[5]), w);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -14,15 +14,17 @@ def random_homography(rng, W, H, rot=0.004, scale=0.003, trans=4.0, persp=2e-6):
     return Hm
 
 
-def synthetic_tracks(rng, P, n_per_pair, W, H, sub_rows=4, sub_cols=4, keep_prob=0.85):
+def synthetic_tracks(rng, P, n_per_pair, W, H, sub_rows=4, sub_cols=4, keep_prob=0.85, local_motion=1.0, homography=None):
     """Un-compacted tracks of P frame pairs in the layout mf_vertex_motion takes.
-    Returns a dict of flat arrays plus per-pair homographies."""
+    Returns a dict of flat arrays plus per-pair homographies.  ``local_motion`` scales the per-feature motion on top
+    of the homography (1e-6: an almost static pair, residuals at the float32 resolution of the coordinates);
+    ``homography``: keyword arguments for ``random_homography``."""
     sw = -(-W // sub_cols)
     sh = -(-H // sub_rows)
     early, late, offset, keep, start, homs = [], [], [], [], [0], []
     for p in range(P):
         n = int(n_per_pair * rng.uniform(0.7, 1.3))
-        Hm = random_homography(rng, W, H)
+        Hm = random_homography(rng, W, H, **(homography or {}))
         sx = rng.integers(0, sub_cols, n)
         sy = rng.integers(0, sub_rows, n)
         off = np.stack([sx * sw, sy * sh], axis=1).astype(np.int32)
@@ -35,7 +37,7 @@ def synthetic_tracks(rng, P, n_per_pair, W, H, sub_rows=4, sub_cols=4, keep_prob
         w = full[:, 0] * Hm[2, 0] + full[:, 1] * Hm[2, 1] + Hm[2, 2]
         lx = (full[:, 0] * Hm[0, 0] + full[:, 1] * Hm[0, 1] + Hm[0, 2]) / w
         ly = (full[:, 0] * Hm[1, 0] + full[:, 1] * Hm[1, 1] + Hm[1, 2]) / w
-        local = rng.normal(0, 0.8, (n, 2)) + rng.normal(0, 1.5, (1, 2)) * (full[:, :1] / W)
+        local = (rng.normal(0, 0.8, (n, 2)) + rng.normal(0, 1.5, (1, 2)) * (full[:, :1] / W)) * local_motion
         lf = (np.stack([lx, ly], axis=1) + local - off).astype(np.float32)
         early.append(ef); late.append(lf); offset.append(off)
         keep.append((rng.uniform(0, 1, n) < keep_prob).astype(np.uint8))

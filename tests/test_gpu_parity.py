@@ -77,6 +77,28 @@ def test_vertex_motion_with_duplicate_values_and_ties():
         assert np.array_equal(outs[0][p], ref) and np.array_equal(outs[1][p], ref)
 
 
+def test_vertex_motion_of_an_almost_static_pair():
+    """Residuals late - H(early) of ~1e-6 px (videos/video-2, pair 0): the float32 velocity shows the last bit of the
+    float64 perspective transform, which OpenCV evaluates with one fused multiply-add per sum (mf_math.cuh persp)."""
+    W, H, R, C = 640, 360, 16, 16
+    rng = np.random.default_rng(32)
+    tr = synth.synthetic_tracks(rng, 6, 5000, W, H, keep_prob=0.95, local_motion=1e-6,
+                                homography=dict(rot=1e-7, scale=1e-7, trans=1e-4, persp=1e-10))
+    core = _core(W, H, R, C)
+    for host in (tr["pair_start"], None):
+        vel = core.vertex_velocities(_dev(tr["early"], core), _dev(tr["late"], core), _dev(tr["offset"], core),
+                                     _dev(tr["keep"], core), _dev(tr["pair_start"], core),
+                                     _dev(tr["homographies"].reshape(-1, 9), core), pair_start_host=host).cpu().numpy()
+        for p in range(6):
+            a, b = tr["pair_start"][p], tr["pair_start"][p + 1]
+            k = tr["keep"][a:b].astype(bool)
+            off = tr["offset"][a:b][k].astype(np.float64)
+            ref = spec.vertex_velocities(tr["early"][a:b][k].astype(np.float64) + off, tr["late"][a:b][k].astype(np.float64) + off,
+                                         tr["homographies"][p], W, H, R, C, 10, 10)
+            assert np.abs(ref).max() < 1e-3
+            assert np.array_equal(vel[p].view(np.uint32), ref.view(np.uint32))
+
+
 def test_vertex_motion_overflowing_candidate_list():
     """More candidates per vertex than the generic path's shared-memory list holds -> re-scan path."""
     W, H, R, C = 640, 360, 4, 4

@@ -107,6 +107,43 @@ def test_spec_matches_port_at_the_bench_geometry():
     assert np.array_equal(port.crop_frames(a, ca)[0], spec.crop_stage(b, cb)[0])
 
 
+def test_perspective_transform_model_matches_opencv_bit_for_bit():
+    """cv2.perspectiveTransform on float64 points (mfs.py:420) keeps every bit, and the residual late - H(early) of
+    an almost static pair exposes the last one: OpenCV's AVX2 / AVX-512 build contracts x*m0 + y*m1 + m2 to
+    fma(x, m0, y*m1) + m2.  The restatement must agree with cv2 itself on every bit (found on videos/video-2, pair 0)."""
+    import cv2
+    rng = np.random.default_rng(31)
+    for k in range(4):
+        M = synth.random_homography(rng, 1920, 1080) if k < 2 else np.eye(3) + rng.normal(0, 0.3, (3, 3))
+        pts = rng.uniform(-50, 2000, (20000, 1, 2))
+        if k == 1:
+            pts = np.round(pts)                                # integer valued corners
+        ref = cv2.perspectiveTransform(pts, M).reshape(-1, 2)
+        px, py = spec.persp_f64(pts[:, 0, 0], pts[:, 0, 1], M)
+        assert np.array_equal(px, ref[:, 0]) and np.array_equal(py, ref[:, 1])
+    a, b, c = (rng.normal(0, 1, 5000) * 10 ** rng.uniform(-6, 6, 5000) for _ in range(3))
+    c[::2] = -(a * b)[::2] * (1 + rng.normal(0, 1e-12, 2500))  # heavy cancellation
+    from fractions import Fraction
+    exact = [float(Fraction(x) * Fraction(y) + Fraction(z)) for x, y, z in zip(a.tolist(), b.tolist(), c.tolist())]
+    assert np.array_equal(spec.fma_f64(a, b, c), np.array(exact))
+
+
+def test_almost_static_pair_spec_equals_port():
+    """Residuals ~1e-6 px: the float32 velocity resolves the last bits of the float64 perspective transform."""
+    rng = np.random.default_rng(32)
+    W, H, R, C = 640, 360, 16, 16
+    tr = synth.synthetic_tracks(rng, 6, 1500, W, H, keep_prob=1.0, local_motion=1e-6,
+                                homography=dict(rot=1e-7, scale=1e-7, trans=1e-4, persp=1e-10))
+    for p in range(6):
+        a, b = tr["pair_start"][p], tr["pair_start"][p + 1]
+        off = tr["offset"][a:b].astype(np.float64)
+        e, l = tr["early"][a:b].astype(np.float64) + off, tr["late"][a:b].astype(np.float64) + off
+        want = port.vertex_velocities_from_matches(port.Params(), W, H, e.reshape(-1, 1, 2), l.reshape(-1, 1, 2), tr["homographies"][p])
+        got = spec.vertex_velocities(e, l, tr["homographies"][p], W, H, R, C, 10, 10)
+        assert np.abs(want).max() < 1e-3
+        assert np.array_equal(got.view(np.uint32), np.asarray(want, np.float32).view(np.uint32))
+
+
 def test_resize_model_matches_opencv():
     import cv2
     rng = np.random.default_rng(9)
