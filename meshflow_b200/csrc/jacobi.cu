@@ -18,22 +18,33 @@
 namespace mf {
 
 __global__ void __launch_bounds__(128) jacobi_coeff_kernel(const double* __restrict__ homographies, int F,
-                                                           int W, int H, int radius, int definition,
+                                                           int W, int H, int radius, int definition, int table_entries,
                                                            double* __restrict__ inv_diag,
                                                            double* __restrict__ two_lambda,
                                                            double* __restrict__ lambda_out) {
+  // exp(-(3k/radius)^2) underflows to exactly 0 beyond |k| ~ 9.1 radius: summing 10 radius either
+  // side equals the reference's sum over all frames.  The CTA evaluates the reach + 1 distinct weights once
+  // (table_entries > 0: they fit the shared-memory table); a frame then adds them in frame order.
+  extern __shared__ double wtab[];
+  const double c = 3.0 / (double)radius;
+  const int reach = 10 * radius + 1;
+  for (int k = threadIdx.x; k < table_entries; k += blockDim.x) {
+    const double a = c * (double)k;
+    wtab[k] = exp(-(a * a));
+  }
+  __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= F) return;
   const double lam = adaptive_lambda(homographies + (size_t)t * 9, W, H, definition);
-  // exp(-(3k/radius)^2) underflows to exactly 0 beyond |k| ~ 9.1 radius: summing 10 radius either
-  // side equals the reference's sum over all frames.
-  const double c = 3.0 / (double)radius;
-  const int reach = 10 * radius + 1;
   const int lo = max(0, t - reach), hi = min(F - 1, t + reach);
   double sum = 0.0;
-  for (int r = lo; r <= hi; ++r) {
-    const double a = c * (double)(t - r);
-    sum += exp(-(a * a));
+  if (table_entries > 0) {
+    for (int r = lo; r <= hi; ++r) sum += wtab[abs(t - r)];
+  } else {
+    for (int r = lo; r <= hi; ++r) {
+      const double a = c * (double)(t - r);
+      sum += exp(-(a * a));
+    }
   }
   const double diag = 1.0 + 2.0 * (lam * sum);
   inv_diag[t] = 1.0 / diag;
@@ -334,10 +345,50 @@ static int set_smem(K kernel, size_t bytes) {
   return MF_OK;
 }
 
+template <int T, int RADIUS>
+static int launch_window(const double* u, double* s, int F, int64_t n_sys, int64_t sys_begin, int64_t n_vert, int iterations,
+                         const double* inv_diag, const double* two_lambda, cudaStream_t st) {
+  const int nt = ((F + T - 1) / T + 31) / 32 * 32;
+  constexpr int hp = (RADIUS + T - 1) / T;
+  const size_t wsmem = ((size_t)T * (nt + 2 * hp) + (size_t)T * nt) * sizeof(double);
+  JacobiWeights wts;
+  for (int k = 0; k < 32; ++k) {
+    const double a = (3.0 / (double)RADIUS) * (double)k;
+    wts.w[k] = k <= RADIUS ? exp(-(a * a)) : 0.0;
+  }
+  auto k = jacobi_window_kernel<T, RADIUS>;
+  if (int e = set_smem(k, wsmem)) return e;
+  k<<<dim3((unsigned)(2 * n_vert)), nt, wsmem, st>>>(u, s, F, n_sys, sys_begin, iterations, inv_diag, two_lambda, wts);
+  return check_launch("jacobi_window");
+}
+
+// The two radii the reference's users run (10: constructor default, 30: BASELINE config 4) take the register-window
+// kernel for every video length; T frames per thread:
+//   20  reads the fewest shared-memory words per FMA: best when the systems outnumber the SMs and the video is long (c4);
+//   5   spreads a system over the most threads: short videos (c2: 300 frames -> 64 threads per system) and the vertex
+//       shard of a multi-GPU run, which has few systems (74 at N = 8 on c2) but world x F frames.
+// Every T performs the same operations in the same order, so the choice never changes a result bit.
+template <int RADIUS>
+static int launch_windowed(const double* u, double* s, int F, int64_t n_sys, int64_t sys_begin, int64_t n_vert, int iterations,
+                           const double* inv_diag, const double* two_lambda, cudaStream_t st) {
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool few = 2 * n_vert < 2 * (int64_t)sms;
+  int T = F >= 2560 ? 20 : F >= 640 ? 10 : 5;
+  if (few) T = F <= 5 * 512 ? 5 : F <= 10 * 512 ? 10 : 20;
+  return T == 5 ? launch_window<5, RADIUS>(u, s, F, n_sys, sys_begin, n_vert, iterations, inv_diag, two_lambda, st)
+       : T == 10 ? launch_window<10, RADIUS>(u, s, F, n_sys, sys_begin, n_vert, iterations, inv_diag, two_lambda, st)
+                 : launch_window<20, RADIUS>(u, s, F, n_sys, sys_begin, n_vert, iterations, inv_diag, two_lambda, st);
+}
+
 template <int RADIUS>
 static int launch_solve(const double* u, double* s, int F, int64_t n_sys, int64_t sys_begin, int64_t n_vert,
                         int radius, int iterations, const double* inv_diag, const double* two_lambda,
                         cudaStream_t st) {
+  if (F > kOnChipMaxFrames) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds %d frames per solve", F, kOnChipMaxFrames);
+  if (radius == 10) return launch_windowed<10>(u, s, F, n_sys, sys_begin, n_vert, iterations, inv_diag, two_lambda, st);
+  if (radius == 30) return launch_windowed<30>(u, s, F, n_sys, sys_begin, n_vert, iterations, inv_diag, two_lambda, st);
   const size_t smem = (size_t)(F + 2 * radius) * sizeof(double2) + (size_t)(2 * radius + 1) * sizeof(double);
   if (smem > 227 * 1024)
     return fail(MF_E_UNSUPPORTED, "jacobi: F=%d radius=%d needs %zu B of shared memory per vertex (max 232448)",
@@ -358,30 +409,7 @@ static int launch_solve(const double* u, double* s, int F, int64_t n_sys, int64_
     auto k = jacobi_solve_kernel<RADIUS, 4>;
     if (int e = set_smem(k, smem)) return e;
     k<<<grid, nt, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
-  } else if (radius == 30 || radius == 10) {
-    // long videos with the two radii the reference's users run: register-window kernel, CTA per system
-    constexpr int T = 20;
-    if (F > T * 512) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds %d frames per solve", F, T * 512);
-    const int nt = ((F + T - 1) / T + 31) / 32 * 32;
-    const int hp = (radius + T - 1) / T;
-    const size_t wsmem = ((size_t)T * (nt + 2 * hp) + (size_t)T * nt) * sizeof(double);
-    JacobiWeights wts;
-    for (int k = 0; k < 32; ++k) {
-      const double a = (3.0 / (double)radius) * (double)k;
-      wts.w[k] = k <= radius ? exp(-(a * a)) : 0.0;
-    }
-    const dim3 wgrid((unsigned)(2 * n_vert));
-    if (radius == 30) {
-      auto k = jacobi_window_kernel<T, 30>;
-      if (int e = set_smem(k, wsmem)) return e;
-      k<<<wgrid, nt, wsmem, st>>>(u, s, F, n_sys, sys_begin, iterations, inv_diag, two_lambda, wts);
-    } else {
-      auto k = jacobi_window_kernel<T, 10>;
-      if (int e = set_smem(k, wsmem)) return e;
-      k<<<wgrid, nt, wsmem, st>>>(u, s, F, n_sys, sys_begin, iterations, inv_diag, two_lambda, wts);
-    }
   } else {
-    if (F > 20 * 512) return fail(MF_E_UNSUPPORTED, "jacobi: F=%d exceeds 10240 frames per solve", F);
     auto k = jacobi_solve_long_kernel<0>;
     if (int e = set_smem(k, smem)) return e;
     k<<<grid, 512, smem, st>>>(u, s, F, n_sys, sys_begin, radius, iterations, inv_diag, two_lambda);
@@ -418,8 +446,9 @@ extern "C" int mf_jacobi_solve(const double* u, const double* homographies, doub
   cudaStream_t st = (cudaStream_t)stream;
   double* inv_diag = (double*)workspace;
   double* two_lambda = (double*)((char*)workspace + mf::align_up((size_t)F * sizeof(double), 256));
-  mf::jacobi_coeff_kernel<<<(F + 127) / 128, 128, 0, st>>>(homographies, F, W, H, radius, definition,
-                                                          inv_diag, two_lambda, lambda_out);
+  const int table_entries = radius <= 500 ? 10 * radius + 2 : 0;      // <= 40 KB of shared memory, else on the fly
+  mf::jacobi_coeff_kernel<<<(F + 127) / 128, 128, (size_t)table_entries * sizeof(double), st>>>(
+      homographies, F, W, H, radius, definition, table_entries, inv_diag, two_lambda, lambda_out);
   if (int e = mf::check_launch("jacobi_coeff")) return e;
   const int64_t n_vert = (sys_end - sys_begin) / 2;
   if (n_vert == 0) return MF_OK;
@@ -430,7 +459,5 @@ extern "C" int mf_jacobi_solve(const double* u, const double* homographies, doub
     return mf::launch_global(u, s, F, n_sys, sys_begin, sys_end - sys_begin, radius, iterations, inv_diag, two_lambda, scratch, st);
   }
   if (n_vert > 2147483647LL) return mf::fail(MF_E_UNSUPPORTED, "mf_jacobi_solve: too many vertices");
-  if (radius == 10)
-    return mf::launch_solve<10>(u, s, F, n_sys, sys_begin, n_vert, radius, iterations, inv_diag, two_lambda, st);
   return mf::launch_solve<0>(u, s, F, n_sys, sys_begin, n_vert, radius, iterations, inv_diag, two_lambda, st);
 }

@@ -507,17 +507,30 @@ __global__ void __launch_bounds__(128) prefix_kernel(const float* __restrict__ v
   double acc = disp0 ? disp0[j] : 0.0;
   disp[j] = acc;
   // The scan itself must stay sequential (float64 additions in frame order, mfs.py:281), but the loads do not
-  // depend on it: eight frames are requested at once so that their L2 round trips overlap (the multi-GPU path
-  // scans world x F frames on every rank).
+  // depend on it: kDepth frames are requested at once and the next batch is requested before the current one is
+  // added, so that the L2 round trips overlap each other and the dependent additions (the multi-GPU path scans
+  // world x F frames on every rank: 2400 frames at N = 8).
+  constexpr int kDepth = 16;
+  float cur[kDepth], nxt[kDepth];
   int t = 0;
-  for (; t + 8 <= P; t += 8) {
-    float v[8];
+  if (P >= kDepth) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = vel[(size_t)(t + k) * n + j];
+    for (int k = 0; k < kDepth; ++k) cur[k] = vel[(size_t)k * n + j];
+  }
+  for (; t + kDepth <= P; t += kDepth) {
+    const bool more = t + 2 * kDepth <= P;
+    if (more) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc = MF_ADD(acc, (double)v[k]);
+      for (int k = 0; k < kDepth; ++k) nxt[k] = vel[(size_t)(t + kDepth + k) * n + j];
+    }
+#pragma unroll
+    for (int k = 0; k < kDepth; ++k) {
+      acc = MF_ADD(acc, (double)cur[k]);
       disp[(size_t)(t + k + 1) * n + j] = acc;
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < kDepth; ++k) cur[k] = nxt[k];
     }
   }
   for (; t < P; ++t) {

@@ -155,6 +155,25 @@ def test_jacobi_vertex_shard_only_touches_its_range():
     assert np.all(out[:, :20] == -7.0) and np.all(out[:, 50:] == -7.0)
 
 
+@pytest.mark.parametrize("F,radius", [(2400, 10), (2400, 30), (4000, 10), (5100, 30)])
+def test_jacobi_small_vertex_shard_of_a_long_video(F, radius):
+    """A multi-GPU vertex shard of a long video: few systems, many frames.  The register-window kernel spreads the
+    frames over more threads then (5 or 10 frames per thread instead of 20); the operations and their order are
+    the same, so the shard equals the single-GPU solve of all vertices bit for bit -- and the oracle to 1e-9."""
+    rng = np.random.default_rng(F + radius)
+    R = 16
+    u, homs = synth.synthetic_paths(rng, F, R, R)
+    core = _core(640, 360, R, R, radius=radius, iterations=30)
+    full = core.stabilized_displacements(_dev(u, core), _dev(homs, core), 1).cpu().numpy().reshape(F, -1, 2)
+    out = torch.full((F, R + 1, R + 1, 2), -7.0, dtype=torch.float64, device=core.device)
+    core.stabilized_displacements(_dev(u, core), _dev(homs, core), 1, vertex_range=(36, 73), out=out)
+    out = out.cpu().numpy().reshape(F, -1, 2)
+    assert np.array_equal(out[:, 36:73], full[:, 36:73])
+    assert np.all(out[:, :36] == -7.0) and np.all(out[:, 73:] == -7.0)
+    ref = spec.jacobi_banded(u[:, 2:3, 2:5], homs, 640, 360, radius, 30, 1)          # vertices 36..38
+    assert np.abs(out[:, 36:39].reshape(ref.shape) - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
 def test_jacobi_rejects_bad_definition():
     from meshflow_b200._cabi import MeshflowNativeError
     core = _core(64, 64, 2, 2)

@@ -82,27 +82,31 @@ def test_video1_full_stabilize_matches_the_reference(golden, stabilizer, definit
 
 @pytest.mark.parametrize("n", OTHER_VIDEOS)
 def test_other_reference_videos_match_the_reference(stabilizer, n, tmp_path):
-    """The reference's other six input clips (246-572 frames of 640x360), ORIGINAL weights, file -> file: same bars
-    as video-1 against ``tests/golden/videoN_full.npz`` (the unmodified reference run in the build container)."""
+    """The reference's other six input clips (246-572 frames of 640x360), file -> file: same bars as video-1 against
+    ``tests/golden/videoN_full.npz`` (the unmodified reference run in the build container) for every
+    ADAPTIVE_WEIGHTS_DEFINITION the record holds (ORIGINAL for all clips, all four for video-10)."""
     video = os.path.join(ROOT, "baseline", "_ref", f"video-{n}.m4v")
     golden = os.path.join(ROOT, "tests", "golden", f"video{n}_full.npz")
     if not os.path.exists(video) or not os.path.exists(golden):
         pytest.skip(f"video-{n} or its golden record not staged")
     g = np.load(golden)
-    if "tuple_0" not in g:
+    definitions = [d for d in range(4) if f"tuple_{d}" in g]
+    if not definitions:
         pytest.skip("golden record incomplete")
-    got = stabilizer.stabilize(video, str(tmp_path / "out.m4v"), 0)
-    if stabilizer.seen_frames_sha != str(g["frames_sha"]):
-        pytest.skip("this box decodes the clip to different pixels than the build container (other FFmpeg build)")
-    r = stabilizer.seen
-    F = int(g["num_frames"])
-    assert len(r["cropped_frames"]) == F
-    assert sha(r["u"]) == str(g["u_sha"]) and sha(r["homographies"]) == str(g["homographies_sha"])
-    V = r["s"].shape[1] * r["s"].shape[2]
-    s_ref = g["s_sample_0"]
-    assert np.abs(r["s"].reshape(F, V, 2)[:, g["sample_vertices"]] - s_ref).max() <= 1e-9 * np.abs(s_ref).max()
-    assert [int(c) for c in r["crop_boundaries"]] == g["crop_0"].tolist()
-    assert sha(np.stack(r["cropped_frames"])) == str(g["cropped_sha_0"]), "cropped pixels differ"
-    ref = g["tuple_0"]
-    for k in range(3):
-        assert abs(float(got[k]) - ref[k]) <= 1e-4 * abs(ref[k]), (k, got, ref)
+    for d in definitions:
+        got = stabilizer.stabilize(video, str(tmp_path / "out.m4v"), d)
+        if stabilizer.seen_frames_sha != str(g["frames_sha"]):
+            pytest.skip("this box decodes the clip to different pixels than the build container (other FFmpeg build)")
+        r = stabilizer.seen
+        F = int(g["num_frames"])
+        assert len(r["cropped_frames"]) == F
+        assert sha(r["u"]) == str(g["u_sha"]), "unstabilized vertex displacements differ from the reference"
+        assert sha(r["homographies"]) == str(g["homographies_sha"])
+        V = r["s"].shape[1] * r["s"].shape[2]
+        s_ref = g[f"s_sample_{d}"]
+        assert np.abs(r["s"].reshape(F, V, 2)[:, g["sample_vertices"]] - s_ref).max() <= 1e-9 * np.abs(s_ref).max()
+        assert [int(c) for c in r["crop_boundaries"]] == g[f"crop_{d}"].tolist()
+        assert sha(np.stack(r["cropped_frames"])) == str(g[f"cropped_sha_{d}"]), f"definition {d}: cropped pixels differ"
+        ref = g[f"tuple_{d}"]
+        for k in range(3):
+            assert abs(float(got[k]) - ref[k]) <= 1e-4 * abs(ref[k]), (d, k, got, ref)
