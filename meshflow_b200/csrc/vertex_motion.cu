@@ -506,35 +506,46 @@ __global__ void __launch_bounds__(128) prefix_kernel(const float* __restrict__ v
   if (j >= n) return;
   double acc = disp0 ? disp0[j] : 0.0;
   disp[j] = acc;
-  // The scan itself must stay sequential (float64 additions in frame order, mfs.py:281), but the loads do not
-  // depend on it: kDepth frames are requested at once and the next batch is requested before the current one is
-  // added, so that the L2 round trips overlap each other and the dependent additions (the multi-GPU path scans
-  // world x F frames on every rank: 2400 frames at N = 8).
+  // The scan itself must stay sequential (float64 additions in frame order, mfs.py:281): one dependent DADD per
+  // frame is the floor.  Everything else is taken off that chain by a three-stage software pipeline over batches
+  // of kDepth frames: batch b + 2 is requested from L2, batch b + 1 (requested one iteration ago) is converted to
+  // float64, batch b is added and stored.  (Measured on a 2400-frame scan -- what every rank of an 8-GPU run does:
+  // 8 loads in flight, converted inside the chain: 111 us; this pipeline: see profiles/r02_prefix_probe.txt.)
   constexpr int kDepth = 16;
-  float cur[kDepth], nxt[kDepth];
-  int t = 0;
-  if (P >= kDepth) {
+  const float* src = vel + j;
+  float f1[kDepth], f2[kDepth];
+  double d0[kDepth];
+  const int nb = P / kDepth;                                 // whole batches
+  auto request = [&](float (&f)[kDepth], int b) {
 #pragma unroll
-    for (int k = 0; k < kDepth; ++k) cur[k] = vel[(size_t)k * n + j];
+    for (int k = 0; k < kDepth; ++k) f[k] = src[(size_t)(b * kDepth + k) * n];
+  };
+  if (nb > 0) request(f1, 0);
+  if (nb > 1) request(f2, 1);
+  if (nb > 0) {
+#pragma unroll
+    for (int k = 0; k < kDepth; ++k) d0[k] = (double)f1[k];
   }
-  for (; t + kDepth <= P; t += kDepth) {
-    const bool more = t + 2 * kDepth <= P;
-    if (more) {
+  for (int b = 0; b < nb; ++b) {
+    // f2 holds batch b + 1 (if any); move it on and request batch b + 2
+    if (b + 1 < nb) {
 #pragma unroll
-      for (int k = 0; k < kDepth; ++k) nxt[k] = vel[(size_t)(t + kDepth + k) * n + j];
+      for (int k = 0; k < kDepth; ++k) f1[k] = f2[k];
     }
+    if (b + 2 < nb) request(f2, b + 2);
+    double* out = disp + (size_t)(b * kDepth + 1) * n + j;
 #pragma unroll
     for (int k = 0; k < kDepth; ++k) {
-      acc = MF_ADD(acc, (double)cur[k]);
-      disp[(size_t)(t + k + 1) * n + j] = acc;
+      acc = MF_ADD(acc, d0[k]);
+      out[(size_t)k * n] = acc;
     }
-    if (more) {
+    if (b + 1 < nb) {
 #pragma unroll
-      for (int k = 0; k < kDepth; ++k) cur[k] = nxt[k];
+      for (int k = 0; k < kDepth; ++k) d0[k] = (double)f1[k];
     }
   }
-  for (; t < P; ++t) {
-    acc = MF_ADD(acc, (double)vel[(size_t)t * n + j]);
+  for (int t = nb * kDepth; t < P; ++t) {
+    acc = MF_ADD(acc, (double)src[(size_t)t * n]);
     disp[(size_t)(t + 1) * n + j] = acc;
   }
 }
