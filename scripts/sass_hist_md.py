@@ -39,7 +39,8 @@ cols = [("r1 warp_fast_kernel", "gpurun_out/r01f_kernels.ncu-rep", "warp_fast"),
         ("r1 crop_resize_rows", "gpurun_out/r01f_kernels.ncu-rep", "crop_resize_rows"),
         ("r2 warp_fast_kernel", "gpurun_out/r02h_twokernel.ncu-rep", "warp_fast"),
         ("r2 crop_resize_rows", "gpurun_out/r02h_twokernel.ncu-rep", "crop_resize_rows"),
-        ("r2 warp_fused_kernel", "gpurun_out/r02h_kernels.ncu-rep", "warp_fused")]
+        ("r2 warp_fused_kernel (3-byte tile)", "gpurun_out/r02h_kernels.ncu-rep", "warp_fused"),
+        ("r2 warp_fused_kernel (final: BGRx tile)", "gpurun_out/r02i_kernels.ncu-rep", "warp_fused")]
 res = [(n,) + hist(rep, k) for n, rep, k in cols]
 ops = collections.Counter()
 for _, h, _, _ in res:
@@ -47,7 +48,7 @@ for _, h, _, _ in res:
         ops[k] = max(ops[k], v)
 lines = ["# Executed instructions per output pixel, pixel kernels, round 1 vs round 2\n",
          "Source: `ncu --set full --import-source on`, `bench.py --frames 60 --steps 1` (60 frames of 1920x1080 per launch, c2 workload);",
-         "`scripts/sass_hist_md.py` over `gpurun_out/r01f_kernels.ncu-rep`, `r02h_twokernel.ncu-rep`, `r02h_kernels.ncu-rep`.",
+         "`scripts/sass_hist_md.py` over `gpurun_out/r01f_kernels.ncu-rep`, `r02h_twokernel.ncu-rep`, `r02h_kernels.ncu-rep`, `r02i_kernels.ncu-rep`.",
          "Unit: warp-instruction lanes per output pixel = executed warp instructions x 32 / (60 x 1920 x 1080); the last",
          "row is thread instructions per pixel (lanes that were actually active).  The fused kernel does the work of the",
          "two kernels to its left (it computes only the pixels inside the crop rectangle, plus one row / column of overlap per tile).\n",
