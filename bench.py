@@ -516,10 +516,11 @@ def run_c2(args):
                    "parallelism": f"frames x{world}, Jacobi vertices x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        # kernels of this library per step: feature_prepare_masks, pair_sort, row_select, median3x3, prefix,
-        # jacobi_coeff, jacobi_solve, cell_setup, tile_sort, cell_spans, row_segments, crop_edges, crop_combine,
-        # resize_table, warp_fused, stability   (two-kernel path: warp_fast + crop_resize_rows instead of warp_fused)
-        "gpu_launches": (16 if fused else 17) * args.steps,
+        # kernels of this library per step (profiles/r02i_launches.csv): feature_prepare_masks, pair_sort, row_select,
+        # median3x3, prefix, jacobi_coeff, jacobi_window, cell_homographies, cell_setup, tile_sort, cell_spans,
+        # row_segments, crop_edges, crop_combine, resize_table, warp_fused, stability
+        # (two-kernel path: warp_fast + crop_resize_rows instead of warp_fused)
+        "gpu_launches": (17 if fused else 18) * args.steps,
         "stages_ms": stage_ms,
         "roofline": {"kernel": pixel_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "kernel_ms_per_launch": ms_pixel,
