@@ -48,6 +48,23 @@ def test_feature_to_vertex_membership_is_bit_exact(emu, W, H, R, C, er, ec):
     assert np.array_equal(m1, m2)
 
 
+def test_kernel_perspective_transform_equals_opencv_bit_for_bit(emu):
+    """mf_math.cuh persp() -- the arithmetic both vertex-motion kernels run -- against cv2.perspectiveTransform on
+    float64 points: every bit (OpenCV's FMA contraction included)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    for k in range(4):
+        M = synth.random_homography(rng, 1920, 1080) if k < 2 else np.eye(3) + rng.normal(0, 0.3, (3, 3))
+        n = 20000
+        x = rng.uniform(-50, 2000, n); y = rng.uniform(-50, 1200, n)
+        if k == 1:
+            x, y = np.round(x), np.round(y)
+        ox = np.zeros(n); oy = np.zeros(n)
+        emu.emu_persp(P(np.ascontiguousarray(M.reshape(-1))), P(x), P(y), n, P(ox), P(oy))
+        ref = cv2.perspectiveTransform(np.stack([x, y], axis=1).reshape(-1, 1, 2), M).reshape(-1, 2)
+        assert np.array_equal(ox, ref[:, 0]) and np.array_equal(oy, ref[:, 1])
+
+
 def test_key_transform_preserves_order_and_roundtrips(emu):
     rng = np.random.default_rng(1)
     v = np.concatenate([rng.normal(0, 1, 500) * 10.0 ** rng.integers(-300, 300, 500), [0.0, 1e-320, -1e-320]])   # (-0.0 sorts below +0.0: harmless, both are zero)
