@@ -244,7 +244,14 @@ __global__ void __launch_bounds__(kMedianThreads) vertex_median_kernel(
 // that column's running rank.
 // =================================================================================================
 static constexpr int kSortMax = 16384;   // features per pair the shared-memory sort holds
-static constexpr int kSelectWarps = 16;
+#ifndef MF_SELECT_WARPS
+#define MF_SELECT_WARPS 16
+#endif
+#ifndef MF_SORT_THREADS
+#define MF_SORT_THREADS 512
+#endif
+static constexpr int kSelectWarps = MF_SELECT_WARPS;
+static constexpr int kSortThreads = MF_SORT_THREADS;       // compare-exchanges per thread and stage: npad / 2 / threads
 static constexpr int kChunks = kSelectWarps / 2;
 
 __global__ void __launch_bounds__(256) feature_prepare_masks_kernel(
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(256) feature_prepare_masks_kernel(
 // Sort of one pair's features by one component.  Elements are single 64-bit words
 // (top 48 key bits | 16-bit local index) so a compare-exchange moves one word; the rare elements whose
 // keys agree in the top 48 bits are put in exact order by a final odd-even pass on the full keys.
-__global__ void __launch_bounds__(1024) pair_sort_kernel(const unsigned long long* __restrict__ keys,
+__global__ void __launch_bounds__(kSortThreads) pair_sort_kernel(const unsigned long long* __restrict__ keys,
                                                          const int32_t* __restrict__ pair_start, int64_t N,
                                                          unsigned long long* __restrict__ sorted_keys,
                                                          uint16_t* __restrict__ perm) {
@@ -659,7 +666,7 @@ extern "C" int mf_vertex_motion(const float* early_xy, const float* late_xy, con
                                             (int)sort_smem);
       if (ce != cudaSuccess) return mf::fail(MF_E_LAUNCH, "pair_sort: shared memory opt-in: %s", cudaGetErrorString(ce));
     }
-    const int sort_threads = npad / 2 < 1024 ? npad / 2 : 1024;
+    const int sort_threads = npad / 2 < mf::kSortThreads ? npad / 2 : mf::kSortThreads;
     mf::pair_sort_kernel<<<dim3((unsigned)P, 2), sort_threads, sort_smem, st>>>(w.keys, pair_start, N, w.sorted_keys,
                                                                                 w.perm);
     if (int e = mf::check_launch("pair_sort")) return e;
