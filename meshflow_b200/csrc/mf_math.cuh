@@ -746,46 +746,97 @@ MF_HD int span_of_row(const Cell& c, const CellSpan& sp, int y, int xlo, int xhi
 // Row segments of one 128-pixel tile row: which cell owns each pixel ("the last cell written wins",
 // mfs.py:1060-1061).  Candidates are visited by descending id; each takes what is still uncovered
 // of its span.  seg[i] = (first x << 16) | cell id, ascending x, seg[0] starts at x0; unused entries
-// are kSegSentinel.  Returns the number of segments, or -1 when more than cap are needed.
+// are kSegSentinel.  finish() returns the number of segments, or -1 when more than CAP are needed.
+//
+// The state lives in registers (round 2 kept interval and segment lists with run-time indices, i.e. in local
+// memory, and the kernel waited on them): the uncovered pixels are a 128-bit mask, a candidate's share is
+// mask & span, its runs start where a set bit follows a clear one, and a new segment is put in its place
+// of the ascending list by one min / max step per slot -- every index is a compile-time constant.
+MF_HD uint32_t shl_sat(uint32_t v, int s) {        // s >= 0; 32 and more shift everything out
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));   // PTX clamps the amount to the register width
+  return r;
+#else
+  return s >= 32 ? 0u : (v << s);
+#endif
+}
+MF_HD uint32_t shr_sat(uint32_t v, int s) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+  return r;
+#else
+  return s >= 32 ? 0u : (v >> s);
+#endif
+}
+MF_HD int lowest_set_bit(uint32_t v) {             // v != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
+template <int CAP>
 struct SegBuilder {
-  int ulo[8], uhi[8], nu;          // uncovered intervals
-  unsigned seg[kSegMax];
-  int ns;
+  static_assert(CAP >= 1 && CAP <= kSegMax, "segment capacity");
+  uint32_t U[4];                 // uncovered pixels: bit i of word w = pixel x0 + 32 w + i
+  unsigned seg[CAP];             // ascending, kSegSentinel behind the ns entries
+  int ns, x0;
   bool overflow;
-  MF_HD void begin(int x0, int x1) { ulo[0] = x0; uhi[0] = x1; nu = 1; ns = 0; overflow = false; }
-  MF_HD void emit(int x, unsigned id, int cap) {
-    if (ns >= cap) { overflow = true; return; }
-    seg[ns++] = ((unsigned)x << 16) | id;
+  MF_HD void begin(int x0_, int x1) {
+    x0 = x0_;
+    const int n = x1 - x0 + 1;                               // 1 .. 128
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int cnt = n - 32 * w;                            // pixels of this word and the following ones
+      U[w] = cnt <= 0 ? 0u : shr_sat(0xffffffffu, cnt >= 32 ? 0 : 32 - cnt);
+    }
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) seg[i] = kSegSentinel;
+    ns = 0; overflow = false;
   }
-  MF_HD void cover(int a, int b, unsigned id, int cap) {
-    const int n0 = nu;
-    for (int i = 0; i < n0; ++i) {
-      const int lo = a > ulo[i] ? a : ulo[i], hi = b < uhi[i] ? b : uhi[i];
-      if (lo > hi) continue;
-      emit(lo, id, cap);
-      const int olo = ulo[i], ohi = uhi[i];
-      if (lo > olo && hi < ohi) {                          // split in two
-        if (nu >= 8) { overflow = true; return; }
-        uhi[i] = lo - 1; ulo[nu] = hi + 1; uhi[nu] = ohi; ++nu;
-      } else if (lo > olo) uhi[i] = lo - 1;
-      else if (hi < ohi) ulo[i] = hi + 1;
-      else { ulo[i] = 1; uhi[i] = 0; }                     // fully covered
+  MF_HD void emit(int x, unsigned id) {
+    if (ns >= CAP) { overflow = true; return; }
+    unsigned v = ((unsigned)x << 16) | id;
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) {                          // sorted insertion: the list stays ascending
+      const unsigned lo = seg[i] < v ? seg[i] : v, hi = seg[i] < v ? v : seg[i];
+      seg[i] = lo; v = hi;
+    }
+    ++ns;
+  }
+  MF_HD void emit_runs(const uint32_t (&T)[4], unsigned id) {
+    uint32_t carry = 0u;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      uint32_t S = T[w] & ~((T[w] << 1) | carry);           // first pixel of every run
+      carry = T[w] >> 31;
+      while (S != 0u) {
+        emit(x0 + 32 * w + lowest_set_bit(S), id);
+        S &= S - 1u;
+      }
     }
   }
-  MF_HD bool done() const {
-    for (int i = 0; i < nu; ++i) if (ulo[i] <= uhi[i]) return false;
-    return true;
-  }
-  MF_HD int finish(int cap) {
-    for (int i = 0; i < nu; ++i) if (ulo[i] <= uhi[i]) emit(ulo[i], kSegNone, cap);
-    if (overflow) return -1;
-    for (int i = 1; i < ns; ++i) {                         // ascending x (high half-word)
-      const unsigned v = seg[i];
-      int j = i - 1;
-      while (j >= 0 && seg[j] > v) { seg[j + 1] = seg[j]; --j; }
-      seg[j + 1] = v;
+  // the candidate `id` takes what is still uncovered of [a, b]  (x0 <= a <= b <= x1)
+  MF_HD void cover(int a, int b, unsigned id, int /*cap*/ = CAP) {
+    const int la = a - x0, lb = b - x0;
+    uint32_t T[4], any = 0u;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int lo = la - 32 * w, hs = 31 - lb + 32 * w;
+      const uint32_t M = shl_sat(0xffffffffu, lo > 0 ? lo : 0) & shr_sat(0xffffffffu, hs > 0 ? hs : 0);
+      T[w] = U[w] & M;
+      U[w] &= ~M;
+      any |= T[w];
     }
-    return ns;
+    if (any != 0u) emit_runs(T, id);
+  }
+  MF_HD bool done() const { return (U[0] | U[1] | U[2] | U[3]) == 0u; }
+  MF_HD int finish(int /*cap*/ = CAP) {
+    if (!done()) emit_runs(U, kSegNone);                     // pixels no candidate covers: default map
+    return overflow ? -1 : ns;
   }
 };
 

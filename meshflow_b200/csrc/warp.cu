@@ -785,9 +785,12 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
     mf::cell_spans_kernel<<<(unsigned)((nspan + 127) / 128), 128, 0, st>>>(w.cells, w.spans, ncells, w.span_rows, w.span_tab);
     if (int e = mf::check_launch("cell_spans")) return e;
     const int64_t nrows = (int64_t)nf * H * tiles_x;
-    mf::row_segments_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
-        w.cells, w.span_tab, w.span_rows, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.segcap, w.rowseg,
-        w.lane_owner);
+    if (w.segcap == 8)
+      mf::row_segments_kernel<8><<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
+          w.cells, w.span_tab, w.span_rows, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.rowseg, w.lane_owner);
+    else
+      mf::row_segments_kernel<mf::kSegMax><<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
+          w.cells, w.span_tab, w.span_rows, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.rowseg, w.lane_owner);
     if (int e = mf::check_launch("row_segments")) return e;
     // one thread per (frame, listed border tile, row of the tile); frames rarely list more than a third of their tiles
     const int64_t nedge = (int64_t)nf * tiles_x * tiles_y * mf::kTileH;

@@ -123,10 +123,12 @@ __device__ __forceinline__ void fill_lanes_from(uint32_t (&packed)[16], int firs
   }
 }
 
+template <int CAP>
 __global__ void __launch_bounds__(128) row_segments_kernel(
     const Cell* __restrict__ cells, const uint32_t* __restrict__ span_tab, int span_rows, const int* __restrict__ tile_count,
-    const uint16_t* __restrict__ tile_list, int nf, int W, int H, int ncell, int tiles_x, int tiles_y, int segcap,
+    const uint16_t* __restrict__ tile_list, int nf, int W, int H, int ncell, int tiles_x, int tiles_y,
     uint32_t* __restrict__ rowseg, uint4* __restrict__ lane_owner) {
+  static_assert(CAP == 8 || CAP == 16, "rowseg entries per tile row (seg_capacity)");
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)nf * H * tiles_x;
   if (idx >= total) return;
@@ -137,8 +139,7 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
   const size_t tile = (size_t)f * tiles_x * tiles_y + (size_t)(y / kTileH) * tiles_x + tx;
   const int craw = __ldg(tile_count + tile);
   const int nraw = craw & kCountMask;
-  uint32_t* out = rowseg + (size_t)idx * segcap;
-  SegBuilder sb;
+  SegBuilder<CAP> sb;                                        // all of it in registers
   sb.begin(x0, x1);
   bool irregular = nraw > kTileCap;
   const Cell* fcells = cells + (size_t)f * ncell;
@@ -166,23 +167,24 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
       if (!use[j] || irregular || done) continue;
       if (spn[j] == kSpanIrregular) { irregular = true; continue; }
       const int a = max((int)(spn[j] & 0xffffu), x0), b = min((int)(spn[j] >> 16), x1);
-      if (a <= b) sb.cover(a, b, (unsigned)id[j], segcap);
+      if (a <= b) sb.cover(a, b, (unsigned)id[j]);
       if (sb.overflow) { irregular = true; continue; }
       if (sb.done()) done = true;
     }
   }
-  int ns = irregular ? -1 : sb.finish(segcap);
+  const int ns = irregular ? -1 : sb.finish();
   if (ns < 0) {
-    out[0] = ((unsigned)x0 << 16) | kSegIrregular;
-    for (int i = 1; i < segcap; ++i) out[i] = kSegSentinel;
-  } else {
-    for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : kSegSentinel;
+    sb.seg[0] = ((unsigned)x0 << 16) | kSegIrregular;
+#pragma unroll
+    for (int i = 1; i < CAP; ++i) sb.seg[i] = kSegSentinel;
   }
+  uint4* out = reinterpret_cast<uint4*>(rowseg + (size_t)idx * CAP);
+#pragma unroll
+  for (int i = 0; i < CAP / 4; ++i) out[i] = make_uint4(sb.seg[4 * i], sb.seg[4 * i + 1], sb.seg[4 * i + 2], sb.seg[4 * i + 3]);
   // owner of each lane's group of four pixels (what the pixel kernel reads: one 16-bit load per lane and row).
-  // Segment by segment instead of lane by lane: a segment that starts r pixels into the tile marks the group that
-  // holds its first pixel as straddling (unless it starts on a group boundary) and owns every group from the next
-  // one on -- two masked fills of the 16 packed words per segment start (a row-tile has 2.3 segments on average;
-  // the lane-by-lane walk with its data-dependent inner loop was 38 % of this kernel's instructions).
+  // Segment by segment: a segment that starts r pixels into the tile marks the group that holds its first pixel as
+  // straddling (unless it starts on a group boundary) and owns every group from the next one on -- two masked fills
+  // of the 16 packed words per segment start (a row-tile has 2.3 segments on average).
   uint32_t packed[16];
   if (ns < 0) {
 #pragma unroll
@@ -191,17 +193,19 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
     const uint32_t first = (sb.seg[0] & 0xffffu) * 0x10001u;
 #pragma unroll
     for (int i = 0; i < 16; ++i) packed[i] = first;
-    for (int i = 1; i < ns; ++i) {
-      const unsigned sg = sb.seg[i];
-      const int r = (int)(sg >> 16) - x0;                    // 1 .. 127
-      fill_lanes_from(packed, r >> 2, kSegStraddle * 0x10001u);
-      fill_lanes_from(packed, (r + 3) >> 2, (sg & 0xffffu) * 0x10001u);
+#pragma unroll
+    for (int i = 1; i < CAP; ++i) {
+      if (i < ns) {
+        const unsigned sg = sb.seg[i];
+        const int r = (int)(sg >> 16) - x0;                  // 1 .. 127
+        fill_lanes_from(packed, r >> 2, kSegStraddle * 0x10001u);
+        fill_lanes_from(packed, (r + 3) >> 2, (sg & 0xffffu) * 0x10001u);
+      }
     }
   }
   uint4* lo = lane_owner + (size_t)idx * 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) lo[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-
 }
 
 // Crop edges of every frame (mfs.py:1075-1098) from the row segments of the tiles that hold a border cell (listed

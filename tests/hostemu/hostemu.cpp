@@ -207,25 +207,28 @@ void emu_warp_frame_fast(const uint8_t* src, const float* vertex_xy, const doubl
     for (int tx = 0; tx < tiles_x; ++tx) {
       const std::vector<int>& l = lists[(y / kTileH) * tiles_x + tx];
       const int x0 = tx * kTileW, x1 = std::min(W - 1, x0 + kTileW - 1);
-      mf::SegBuilder sb; sb.begin(x0, x1);
-      bool irregular = (int)l.size() > kTileCap;
-      for (size_t k = 0; k < l.size() && !irregular; ++k) {
-        const int id = l[k];
-        const mf::Cell& c = cells[id];
-        if (y < c.by0 || y > c.by1 || x1 < c.bx0 || x0 > c.bx1) continue;
-        if (!spans[id].regular) { irregular = true; break; }
-        int a, b;
-        const int st = mf::span_of_row(c, spans[id], y, std::max(x0, c.bx0), std::min(x1, c.bx1), a, b);
-        if (st == 2) { irregular = true; break; }
-        if (st == 0) sb.cover(a, b, (unsigned)id, segcap);
-        if (sb.overflow) { irregular = true; break; }
-        if (sb.done()) break;
-      }
-      const int ns = irregular ? -1 : sb.finish(segcap);
       unsigned* out = &rowseg[((size_t)y * tiles_x + tx) * segcap];
       stats[4]++;
-      if (ns < 0) { out[0] = ((unsigned)x0 << 16) | mf::kSegIrregular; for (int i = 1; i < segcap; ++i) out[i] = mf::kSegSentinel; stats[3]++; }
-      else for (int i = 0; i < segcap; ++i) out[i] = i < ns ? sb.seg[i] : mf::kSegSentinel;
+      auto build = [&](auto& sb) {
+        sb.begin(x0, x1);
+        bool irregular = (int)l.size() > kTileCap;
+        for (size_t k = 0; k < l.size() && !irregular; ++k) {
+          const int id = l[k];
+          const mf::Cell& c = cells[id];
+          if (y < c.by0 || y > c.by1 || x1 < c.bx0 || x0 > c.bx1) continue;
+          if (!spans[id].regular) { irregular = true; break; }
+          int a, b;
+          const int st = mf::span_of_row(c, spans[id], y, std::max(x0, c.bx0), std::min(x1, c.bx1), a, b);
+          if (st == 2) { irregular = true; break; }
+          if (st == 0) sb.cover(a, b, (unsigned)id);
+          if (sb.overflow) { irregular = true; break; }
+          if (sb.done()) break;
+        }
+        const int ns = irregular ? -1 : sb.finish();
+        if (ns < 0) { out[0] = ((unsigned)x0 << 16) | mf::kSegIrregular; for (int i = 1; i < segcap; ++i) out[i] = mf::kSegSentinel; stats[3]++; }
+        else for (int i = 0; i < segcap; ++i) out[i] = sb.seg[i];
+      };
+      if (segcap == 8) { mf::SegBuilder<8> sb; build(sb); } else { mf::SegBuilder<16> sb; build(sb); }
     }
   // crop edges from the row segments of tiles that hold a border cell (crop_edges_kernel)
   int crop[4] = {0, 0, W - 1, H - 1};
@@ -358,15 +361,21 @@ void emu_cell_fast_info(const float* vertex_xy, const double* u, const double* s
 // seg_owner / seg_group_owner for comparison with a brute-force resolution.
 int emu_resolve_segments(int x0, int x1, int n, const int* a, const int* b, const int* ids, int cap, unsigned* seg_out,
                          unsigned* owner_px, unsigned* owner_group) {
-  mf::SegBuilder sb; sb.begin(x0, x1);
-  for (int k = 0; k < n && !sb.overflow && !sb.done(); ++k) {
-    const int lo = std::max(a[k], x0), hi = std::min(b[k], x1);
-    if (lo <= hi) sb.cover(lo, hi, (unsigned)ids[k], cap);
-  }
-  const int ns = sb.finish(cap);
-  if (ns < 0) return -1;
   unsigned seg[mf::kSegMax];
-  for (int i = 0; i < mf::kSegMax; ++i) { seg[i] = i < ns ? sb.seg[i] : mf::kSegSentinel; seg_out[i] = seg[i]; }
+  auto build = [&](auto& sb) -> int {
+    sb.begin(x0, x1);
+    for (int k = 0; k < n && !sb.overflow && !sb.done(); ++k) {
+      const int lo = std::max(a[k], x0), hi = std::min(b[k], x1);
+      if (lo <= hi) sb.cover(lo, hi, (unsigned)ids[k]);
+    }
+    const int ns = sb.finish();
+    for (int i = 0; i < mf::kSegMax; ++i) seg[i] = (ns >= 0 && i < cap) ? sb.seg[i < cap ? i : 0] : mf::kSegSentinel;
+    return ns;
+  };
+  int ns;
+  if (cap == 8) { mf::SegBuilder<8> sb; ns = build(sb); } else { mf::SegBuilder<16> sb; ns = build(sb); }
+  if (ns < 0) return -1;
+  for (int i = 0; i < mf::kSegMax; ++i) seg_out[i] = seg[i];
   for (int x = x0; x <= x1; ++x) owner_px[x - x0] = mf::seg_owner(seg, cap, x);
   for (int g = x0; g <= x1; g += 4) {
     bool strad;

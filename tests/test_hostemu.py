@@ -251,9 +251,11 @@ def test_crop_edges_from_row_segments_equal_the_pixel_scan(emu, W, H, R, C):
 def test_segment_resolution_matches_brute_force(emu):
     """'The last cell written wins': random overlapping intervals in priority order against a per-pixel loop."""
     rng = np.random.default_rng(5)
-    x0, x1 = 256, 383
     overflowed = 0
-    for trial in range(400):
+    for trial in range(1200):
+        # whole tiles and the narrower last tile of a row (1 .. 128 pixels), word boundaries of the 128-bit mask included
+        x0 = 128 * int(rng.integers(0, 30))
+        x1 = x0 + (127 if trial % 3 else int(rng.choice([0, 1, 30, 31, 32, 33, 63, 64, 65, 95, 96, 97, 126, int(rng.integers(0, 128))])))
         n = int(rng.integers(0, 12))
         a = rng.integers(x0 - 30, x1 + 10, n).astype(np.int32)
         b = (a + rng.integers(-3, 90, n)).astype(np.int32)
@@ -261,7 +263,8 @@ def test_segment_resolution_matches_brute_force(emu):
         cap = 8 if trial % 2 else 16
         seg = np.zeros(16, np.uint32); opx = np.zeros(128, np.uint32); ogr = np.zeros(32, np.uint32)
         ns = emu.emu_resolve_segments(x0, x1, n, P(a), P(b), P(ids), cap, P(seg), P(opx), P(ogr))
-        ref = np.full(128, 0xFFFF, np.uint32)
+        npx = x1 - x0 + 1
+        ref = np.full(npx, 0xFFFF, np.uint32)
         for k in range(n - 1, -1, -1):                       # lowest priority first, higher ones overwrite
             lo, hi = max(int(a[k]), x0), min(int(b[k]), x1)
             if lo <= hi:
@@ -271,13 +274,15 @@ def test_segment_resolution_matches_brute_force(emu):
             overflowed += 1
             assert changes > cap // 2                        # only gives up when there really are many segments
             continue
-        assert np.array_equal(opx, ref)
-        for g in range(32):
+        assert ns == changes                                 # one segment per run of equal owners
+        assert np.array_equal(opx[:npx], ref)
+        for g in range((npx + 3) // 4):
             grp = ref[4 * g:4 * g + 4]
             want = 0xFFFD if (grp != grp[0]).any() else grp[0]
             assert ogr[g] == want
         assert (np.diff((seg[:ns] >> 16).astype(np.int64)) > 0).all() and (seg[ns:] == 0xFFFFFFFF).all()
-    assert overflowed < 200
+        assert seg[0] >> 16 == x0
+    assert overflowed < 600
 
 
 @pytest.mark.parametrize("W,H,R,C", [(1920, 1080, 16, 16), (3840, 2160, 16, 16), (1280, 720, 64, 64), (1920, 1080, 32, 32)])
