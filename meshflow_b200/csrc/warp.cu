@@ -792,9 +792,10 @@ static int prepare_cells(const double* u, const double* s, const float* vertex_x
       mf::row_segments_kernel<mf::kSegMax><<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
           w.cells, w.span_tab, w.span_rows, w.tile_count, w.tile_list, nf, W, H, R * C, tiles_x, tiles_y, w.rowseg, w.lane_owner);
     if (int e = mf::check_launch("row_segments")) return e;
-    // one thread per (frame, listed border tile, row of the tile); frames rarely list more than a third of their tiles
-    const int64_t nedge = (int64_t)nf * tiles_x * tiles_y * mf::kTileH;
-    mf::crop_edges_kernel<<<(unsigned)((nedge + 127) / 128), 128, 0, st>>>(
+    // one thread per (frame, listed border tile, row of the tile); a CTA strides over its frame's list
+    const int all_blocks = (tiles_x * tiles_y + mf::kCropEdgeSlotsPerCta - 1) / mf::kCropEdgeSlotsPerCta;
+    const int slot_blocks = all_blocks < mf::kCropEdgeSlotBlocks ? all_blocks : mf::kCropEdgeSlotBlocks;
+    mf::crop_edges_kernel<<<dim3((unsigned)slot_blocks, (unsigned)nf), 128, 0, st>>>(
         w.cells, w.tile_count, w.tile_list, w.rowseg, w.edge_count, w.edge_tiles, nf, W, H, R * C, tiles_x, tiles_y, w.segcap,
         crop_out);
     return mf::check_launch("crop_edges");

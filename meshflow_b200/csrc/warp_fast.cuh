@@ -209,39 +209,45 @@ __global__ void __launch_bounds__(128) row_segments_kernel(
 }
 
 // Crop edges of every frame (mfs.py:1075-1098) from the row segments of the tiles that hold a border cell (listed
-// per frame by cell_setup_kernel): one thread per (frame, listed tile, row of the tile).  A kernel of its own so
-// that the float64 registers of the band search do not burden the segment builder.
+// per frame by tile_sort_kernel): one thread per (frame, listed tile, row of the tile).  A kernel of its own so
+// that the float64 registers of the band search do not burden the segment builder.  Grid = (kCropEdgeSlotBlocks,
+// frames): a CTA takes 128 / kTileH listed tiles (all their rows) per pass and strides over the frame's list, so that
+// CTAs are only launched for tiles that can be listed (a thread per row of every tile of the frame meant 75 % CTAs
+// that left at once).
+static constexpr int kCropEdgeSlotBlocks = 32;               // 32 x 16 = 512 listed tiles per pass; frames with more loop
+static constexpr int kCropEdgeSlotsPerCta = 128 / kTileH;
+static_assert(128 % kTileH == 0, "crop_edges_kernel: whole tiles per CTA");
+
 __global__ void __launch_bounds__(128) crop_edges_kernel(
     const Cell* __restrict__ cells, const int* __restrict__ tile_count, const uint16_t* __restrict__ tile_list,
     const uint32_t* __restrict__ rowseg, const int* __restrict__ edge_count, const uint16_t* __restrict__ edge_tiles, int nf,
     int W, int H, int ncell, int tiles_x, int tiles_y, int segcap, int32_t* __restrict__ crop_out) {
   const int ntiles = tiles_x * tiles_y;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)nf * ntiles * kTileH) return;
-  const int ry = (int)(idx % kTileH);
-  const int64_t fs = idx / kTileH;
-  const int slot = (int)(fs % ntiles), f = (int)(fs / ntiles);
-  if (slot >= __ldg(edge_count + f)) return;                // listed tiles come first: whole warps leave here
-  const int t = (int)__ldg(edge_tiles + (size_t)f * ntiles + slot);
-  const int ty = t / tiles_x, tx = t - ty * tiles_x;
-  const int y = ty * kTileH + ry;
-  if (y >= H) return;
-  const size_t tile = (size_t)f * ntiles + t;
-  const int craw = __ldg(tile_count + tile);
-  const int x0 = tx * kTileW, x1 = min(W - 1, x0 + kTileW - 1);
-  const uint32_t* rs = rowseg + (((size_t)f * H + y) * tiles_x + tx) * segcap;
-  unsigned seg[kSegMax];                                     // the whole list in independent 16-byte loads (segcap is 8 or 16)
+  const int f = blockIdx.y;
+  const int ry = threadIdx.x % kTileH;
+  const int listed = __ldg(edge_count + f);
+  for (int slot = blockIdx.x * kCropEdgeSlotsPerCta + threadIdx.x / kTileH; slot < listed; slot += gridDim.x * kCropEdgeSlotsPerCta) {
+    const int t = (int)__ldg(edge_tiles + (size_t)f * ntiles + slot);
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int y = ty * kTileH + ry;
+    if (y >= H) continue;
+    const size_t tile = (size_t)f * ntiles + t;
+    const int craw = __ldg(tile_count + tile);
+    const int x0 = tx * kTileW, x1 = min(W - 1, x0 + kTileW - 1);
+    const uint32_t* rs = rowseg + (((size_t)f * H + y) * tiles_x + tx) * segcap;
+    unsigned seg[kSegMax];                                   // the whole list in independent 16-byte loads (segcap is 8 or 16)
 #pragma unroll
-  for (int i = 0; i < kSegMax / 4; ++i) {
-    const uint4 q = 4 * i < segcap ? __ldg(reinterpret_cast<const uint4*>(rs) + i) : make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
-    seg[4 * i] = q.x; seg[4 * i + 1] = q.y; seg[4 * i + 2] = q.z; seg[4 * i + 3] = q.w;
+    for (int i = 0; i < kSegMax / 4; ++i) {
+      const uint4 q = 4 * i < segcap ? __ldg(reinterpret_cast<const uint4*>(rs) + i) : make_uint4(kSegSentinel, kSegSentinel, kSegSentinel, kSegSentinel);
+      seg[4 * i] = q.x; seg[4 * i + 1] = q.y; seg[4 * i + 2] = q.z; seg[4 * i + 3] = q.w;
+    }
+    int ns = 0;
+#pragma unroll
+    for (int i = 0; i < kSegMax; ++i) ns += seg[i] != kSegSentinel ? 1 : 0;    // entries are contiguous from the front
+    if ((seg[0] & 0xffffu) == kSegIrregular) ns = -1;
+    row_crop_edges(cells + (size_t)f * ncell, tile_list + tile * kTileCap, craw & kCountMask, ncell, seg, ns, x0, x1, y, W, H,
+                   crop_out + 4 * f);
   }
-  int ns = 0;
-#pragma unroll
-  for (int i = 0; i < kSegMax; ++i) ns += seg[i] != kSegSentinel ? 1 : 0;      // entries are contiguous from the front
-  if ((seg[0] & 0xffffu) == kSegIrregular) ns = -1;
-  row_crop_edges(cells + (size_t)f * ncell, tile_list + tile * kTileCap, craw & kCountMask, ncell, seg, ns, x0, x1, y, W, H,
-                 crop_out + 4 * f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
