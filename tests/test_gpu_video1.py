@@ -84,7 +84,7 @@ def test_video1_full_stabilize_matches_the_reference(golden, stabilizer, definit
 def test_other_reference_videos_match_the_reference(stabilizer, n, tmp_path):
     """The reference's other six input clips (246-572 frames of 640x360), file -> file: same bars as video-1 against
     ``tests/golden/videoN_full.npz`` (the unmodified reference run in the build container) for every
-    ADAPTIVE_WEIGHTS_DEFINITION the record holds (ORIGINAL for all clips, all four for video-10)."""
+    ADAPTIVE_WEIGHTS_DEFINITION the record holds (all four for video-2, -5 and -10, ORIGINAL for the rest)."""
     video = os.path.join(ROOT, "baseline", "_ref", f"video-{n}.m4v")
     golden = os.path.join(ROOT, "tests", "golden", f"video{n}_full.npz")
     if not os.path.exists(video) or not os.path.exists(golden):
